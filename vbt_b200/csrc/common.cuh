@@ -1,0 +1,43 @@
+// Shared helpers for libvbt_b200.so (error reporting, launch accounting).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/vbt_b200.h"
+
+namespace vbt {
+
+void set_error(const char* fmt, ...);
+void count_launches(long long n);
+int ensure_device();  // VBT_OK when an sm_100 device is current, else VBT_ECUDA
+
+#define VBT_CHECK_CUDA(expr)                                                          \
+  do {                                                                                \
+    cudaError_t e__ = (expr);                                                         \
+    if (e__ != cudaSuccess) {                                                         \
+      vbt::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                     __LINE__);                                                       \
+      return VBT_ECUDA;                                                               \
+    }                                                                                 \
+  } while (0)
+
+#define VBT_REQUIRE(cond, ...)      \
+  do {                              \
+    if (!(cond)) {                  \
+      vbt::set_error(__VA_ARGS__);  \
+      return VBT_EINVAL;            \
+    }                               \
+  } while (0)
+
+// call after every kernel launch: records it and surfaces launch-configuration errors
+#define VBT_LAUNCHED(n)                       \
+  do {                                        \
+    vbt::count_launches(n);                   \
+    VBT_CHECK_CUDA(cudaPeekAtLastError());    \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace vbt

@@ -1,0 +1,90 @@
+// Device-side description of one EfficientDet-Lite model: the layer program written by
+// vbt_b200/effdet.py, its weights, anchors and output quantisation.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace vbt {
+
+// Blob layout (little endian):
+//   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
+constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
+constexpr int kBlobVersion = 2;
+
+struct BlobHeader {
+  uint32_t magic;
+  int32_t version;
+  int32_t input_size;      // S
+  int32_t n_anchors;       // N
+  int32_t n_anchors_pad;   // N rounded up to 16: row stride of the raw outputs
+  int32_t n_classes;
+  int32_t n_ops;
+  int32_t n_tensors;
+  int64_t ws_bytes_per_frame;   // activation workspace per frame
+  int64_t data_offset;          // byte offset of the data section from blob start
+  int64_t data_bytes;
+  int64_t anchors_off;          // f32 [N,4] (ycentre,xcentre,h,w), offsets into data
+  int64_t exp_lut_off;          // f32 [256]  exp(dequant(q)) for q = -128..127
+  float box_scale;              // dequantisation of the raw box output
+  int32_t box_zp;
+  int32_t in_zp;                // uint8 input zero point (127)
+  int32_t reserved[7];
+};
+
+enum OpType : int32_t {
+  OP_STEM = 1,      // 3x3 s2 conv on the uint8 input, ReLU6
+  OP_PW = 2,        // 1x1 conv (+ optional fused quantised residual add)
+  OP_DW = 3,        // depthwise kxk
+  OP_ADD = 4,       // quantised n-ary add with resampling (BiFPN fusion), ReLU6
+  OP_MAXPOOL = 5,   // 3x3 s2 SAME
+  OP_LOGISTIC = 6,  // int8 LUT applied in place on the class output
+};
+
+enum Resample : int32_t { RS_NONE = 0, RS_UP_NEAREST = 1, RS_DOWN_MAXPOOL = 2 };
+
+struct OpRecord {
+  int32_t type;
+  int32_t in[3];           // tensor ids (-1 unused); PW: in[1] = residual
+  int32_t out;
+  int32_t n_in;
+  int32_t k, stride;
+  int32_t cin, cout;       // logical channels
+  int32_t cin_p, cout_p;   // physical (padded to 16) channels
+  int32_t h_in, w_in, h_out, w_out;
+  int32_t zp_in[3];
+  int32_t zp_out;
+  int32_t act_lo, act_hi;  // clamp of the int8 result
+  int32_t pad_top, pad_left;
+  int64_t w_off, bias_off, scale_off, lut_off;   // data-section byte offsets (-1 none)
+  // OP_ADD / fused residual: integer rescale  out = clamp(((sum_i (x_i - zp_i)*mult_i)
+  //                                             + round) >> shift) + zp_out)
+  int32_t add_mult[3];
+  int32_t add_shift;
+  int32_t resample[3];
+  int32_t in_h[3], in_w[3];
+  // output placement: element offset of pixel p of frame b =
+  //   out_off(b) + p * out_pix_stride ; out_off(b) = tensor base + b * out_batch_stride
+  int32_t out_kind;        // 0 workspace tensor, 1 raw class output, 2 raw box output
+  int32_t out_pix_stride;
+  int64_t out_elem_offset; // within-frame element offset (level offset for the heads)
+  int32_t reserved[6];
+};
+
+struct TensorRecord {
+  int64_t ws_offset;   // per-frame byte offset inside the workspace
+  int32_t h, w, c, c_p;
+};
+
+}  // namespace vbt
+
+struct vbt_model {
+  vbt::BlobHeader hdr;
+  std::vector<vbt::OpRecord> ops;
+  std::vector<vbt::TensorRecord> tensors;
+  uint8_t* dev_data = nullptr;     // the blob's data section on the device
+  const float* dev_anchors = nullptr;
+  const float* dev_exp_lut = nullptr;
+  int kernels_per_detect = 0;
+  int device = -1;
+};

@@ -1,0 +1,676 @@
+// K7 -- OC-SORT plate tracker, one warp per video, state resident on the device.
+//
+// replaces: ocsort.OCSort(max_age=30, asso_func="diou", iou_threshold=0.1) and
+// tracker.update(dets, []) (track.py:157,186-187) plus the row assembly of
+// track.py:189-234.  The package source is not part of the reference checkout; the
+// algorithm restated here is the published OC-SORT (observation-centric re-update,
+// velocity-direction cost, second association round on last observations) over a
+// filterpy-style 7-state constant-velocity Kalman filter -- see oracle/ocsort.py for the
+// CPU restatement this kernel is checked against and DESIGN.md for what is pinned.
+//
+// Layout: lanes of the warp own tracks (Kalman predict / correct are lane-parallel),
+// lane 0 runs the association bookkeeping.  fp64, -fmad=false, dense 7x7 products
+// accumulated k-ascending so results are bit-identical to the oracle.
+// Latency-bound sequential recurrence over the frame axis: no roofline (us per frame).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int kMaxT = 64;   // live tracks per video
+constexpr int kMaxD = 32;   // detections per frame
+constexpr int NX = 7, NZ = 4;
+
+struct Trk {
+  double x[NX];
+  double P[NX * NX];
+  double fx[NX];            // state frozen at the first missed frame
+  double fP[NX * NX];
+  double prev_z[NZ];        // measurement the next re-update interpolates from
+  double last_obs[5];
+  double obs_box[4][5];     // observations of the last ages, slot = age & 3
+  double vel[2];            // (dy, dx) unit direction
+  double conf, cls;
+  int obs_age[4];
+  int id, tsu, hits, hit_streak, age;
+  int has_last, has_vel, observed, has_frozen, missed, n_obs;
+};
+
+struct Video {
+  int frame_count, next_id, n_tracks, status;
+  int order[kMaxT];         // slot of the i-th tracker in list order
+  unsigned char used[kMaxT];
+};
+
+struct Params {
+  double det_thresh, iou_threshold, inertia;
+  int max_age, min_hits, delta_t, vdc_cls;
+};
+
+__device__ __forceinline__ void mm(const double* a, const double* b, double* c, int n, int m,
+                                   int p) {   // c[n,p] = a[n,m] * b[m,p], k ascending
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < p; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < m; ++k) acc = acc + a[i * m + k] * b[k * p + j];
+      c[i * p + j] = acc;
+    }
+}
+
+// c[n,p] = a[n,m] * b[p,m]^T
+__device__ __forceinline__ void mmt(const double* a, const double* b, double* c, int n, int m,
+                                    int p) {
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j < p; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < m; ++k) acc = acc + a[i * m + k] * b[j * m + k];
+      c[i * p + j] = acc;
+    }
+}
+
+__device__ void kf_predict(double* x, double* P) {
+  double F[NX * NX], t[NX * NX], nx[NX];
+  for (int i = 0; i < NX * NX; ++i) F[i] = 0.0;
+  for (int i = 0; i < NX; ++i) F[i * NX + i] = 1.0;
+  F[0 * NX + 4] = F[1 * NX + 5] = F[2 * NX + 6] = 1.0;
+  mm(F, x, nx, NX, NX, 1);
+  for (int i = 0; i < NX; ++i) x[i] = nx[i];
+  mm(F, P, t, NX, NX, NX);
+  mmt(t, F, P, NX, NX, NX);
+  const double q[NX] = {1.0, 1.0, 1.0, 1.0, 0.01, 0.01, 0.0001};
+  for (int i = 0; i < NX; ++i) P[i * NX + i] = P[i * NX + i] + q[i];
+}
+
+__device__ void kf_correct(double* x, double* P, const double* z) {
+  double H[NZ * NX], R[NZ * NZ];
+  for (int i = 0; i < NZ * NX; ++i) H[i] = 0.0;
+  for (int i = 0; i < NZ; ++i) H[i * NX + i] = 1.0;
+  for (int i = 0; i < NZ * NZ; ++i) R[i] = 0.0;
+  R[0] = 1.0; R[5] = 1.0; R[10] = 10.0; R[15] = 10.0;
+  double hx[NZ], y[NZ], pht[NX * NZ], s[NZ * NZ], si[NZ * NZ], k[NX * NZ], ky[NX];
+  mm(H, x, hx, NZ, NX, 1);
+  for (int i = 0; i < NZ; ++i) y[i] = z[i] - hx[i];
+  mmt(P, H, pht, NX, NX, NZ);
+  mm(H, pht, s, NZ, NX, NZ);
+  for (int i = 0; i < NZ * NZ; ++i) { s[i] = s[i] + R[i]; si[i] = 0.0; }
+  for (int i = 0; i < NZ; ++i) si[i * NZ + i] = 1.0 / s[i * NZ + i];  // S is diagonal
+  mm(pht, si, k, NX, NZ, NZ);
+  mm(k, y, ky, NX, NZ, 1);
+  for (int i = 0; i < NX; ++i) x[i] = x[i] + ky[i];
+  double ikh[NX * NX], t1[NX * NX], t2[NX * NX], kr[NX * NZ], krk[NX * NX];
+  mm(k, H, ikh, NX, NZ, NX);
+  for (int i = 0; i < NX; ++i)
+    for (int j = 0; j < NX; ++j) ikh[i * NX + j] = ((i == j) ? 1.0 : 0.0) - ikh[i * NX + j];
+  mm(ikh, P, t1, NX, NX, NX);
+  mmt(t1, ikh, t2, NX, NX, NX);
+  mm(k, R, kr, NX, NZ, NZ);
+  mmt(kr, k, krk, NX, NZ, NX);
+  for (int i = 0; i < NX * NX; ++i) P[i] = t2[i] + krk[i];
+}
+
+__device__ __forceinline__ void box_to_z(const double* b, double* z) {
+  double w = b[2] - b[0], h = b[3] - b[1];
+  z[0] = b[0] + w / 2.0; z[1] = b[1] + h / 2.0; z[2] = w * h; z[3] = w / (h + 1e-6);
+}
+
+__device__ __forceinline__ void x_to_box(const double* x, double* b) {
+  double w = sqrt(x[2] * x[3]);
+  double h = x[2] / w;
+  b[0] = x[0] - w / 2.0; b[1] = x[1] - h / 2.0; b[2] = x[0] + w / 2.0; b[3] = x[1] + h / 2.0;
+}
+
+__device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no observation
+  if (!z) {
+    if (t.observed) {
+      for (int i = 0; i < NX; ++i) t.fx[i] = t.x[i];
+      for (int i = 0; i < NX * NX; ++i) t.fP[i] = t.P[i];
+      t.has_frozen = 1;
+    }
+    t.observed = 0;
+    t.missed += 1;
+    return;
+  }
+  if (!t.observed && t.has_frozen) {        // observation-centric re-update
+    for (int i = 0; i < NX; ++i) t.x[i] = t.fx[i];
+    for (int i = 0; i < NX * NX; ++i) t.P[i] = t.fP[i];
+    int gap = t.missed + 1;
+    double x1 = t.prev_z[0], y1 = t.prev_z[1], s1 = t.prev_z[2], r1 = t.prev_z[3];
+    double w1 = sqrt(s1 * r1), h1 = sqrt(s1 / r1);
+    double w2 = sqrt(z[2] * z[3]), h2 = sqrt(z[2] / z[3]);
+    double dx = (z[0] - x1) / gap, dy = (z[1] - y1) / gap;
+    double dw = (w2 - w1) / gap, dh = (h2 - h1) / gap;
+    double v[NZ] = {0, 0, 0, 0};
+    for (int i = 0; i < gap; ++i) {
+      double w = w1 + (i + 1) * dw, h = h1 + (i + 1) * dh;
+      v[0] = x1 + (i + 1) * dx; v[1] = y1 + (i + 1) * dy; v[2] = w * h; v[3] = w / h;
+      kf_correct(t.x, t.P, v);
+      if (i != gap - 1) kf_predict(t.x, t.P);
+    }
+    for (int i = 0; i < NZ; ++i) t.prev_z[i] = v[i];   // history ends with the virtual box
+  } else {
+    for (int i = 0; i < NZ; ++i) t.prev_z[i] = z[i];
+  }
+  t.observed = 1;
+  t.missed = 0;
+  kf_correct(t.x, t.P, z);
+}
+
+__device__ void trk_predict(Trk& t, double* box) {
+  if (t.x[6] + t.x[2] <= 0) t.x[6] *= 0.0;
+  kf_predict(t.x, t.P);
+  t.age += 1;
+  if (t.tsu > 0) t.hit_streak = 0;
+  t.tsu += 1;
+  x_to_box(t.x, box);
+}
+
+__device__ __forceinline__ const double* obs_at(const Trk& t, int age) {
+  if (age < 0) return nullptr;
+  return (t.obs_age[age & 3] == age) ? t.obs_box[age & 3] : nullptr;
+}
+
+// observation delta_t frames back (or the nearest newer one), else the latest, else null
+__device__ const double* k_previous(const Trk& t, int k) {
+  if (t.n_obs == 0) return nullptr;
+  for (int i = 0; i < k; ++i) {
+    const double* o = obs_at(t, t.age - (k - i));
+    if (o) return o;
+  }
+  return t.last_obs;
+}
+
+__device__ void trk_update(Trk& t, const double* det, int delta_t) {  // det: 6 doubles or null
+  if (!det) { kf_update(t, nullptr); return; }
+  t.conf = det[4];
+  t.cls = det[5];
+  if (t.has_last) {
+    double sum = t.last_obs[0] + t.last_obs[1] + t.last_obs[2] + t.last_obs[3] + t.last_obs[4];
+    if (sum >= 0) {
+      const double* prev = nullptr;
+      for (int i = 0; i < delta_t && !prev; ++i) prev = obs_at(t, t.age - (delta_t - i));
+      if (!prev) prev = t.last_obs;
+      double cx1 = (prev[0] + prev[2]) / 2.0, cy1 = (prev[1] + prev[3]) / 2.0;
+      double cx2 = (det[0] + det[2]) / 2.0, cy2 = (det[1] + det[3]) / 2.0;
+      double dy = cy2 - cy1, dx = cx2 - cx1;
+      double n = sqrt(dy * dy + dx * dx) + 1e-6;
+      t.vel[0] = dy / n; t.vel[1] = dx / n;
+      t.has_vel = 1;
+    }
+  }
+  for (int i = 0; i < 5; ++i) { t.last_obs[i] = det[i]; t.obs_box[t.age & 3][i] = det[i]; }
+  t.obs_age[t.age & 3] = t.age;
+  t.has_last = 1;
+  t.n_obs += 1;
+  t.tsu = 0;
+  t.hits += 1;
+  t.hit_streak += 1;
+  double z[NZ];
+  box_to_z(det, z);
+  kf_update(t, z);
+}
+
+__device__ void trk_init(Trk& t, const double* det, int id) {
+  for (int i = 0; i < NX; ++i) t.x[i] = 0.0;
+  double z[NZ];
+  box_to_z(det, z);
+  for (int i = 0; i < NZ; ++i) t.x[i] = z[i];
+  const double p0[NX] = {10.0, 10.0, 10.0, 10.0, 10000.0, 10000.0, 10000.0};
+  for (int i = 0; i < NX * NX; ++i) t.P[i] = 0.0;
+  for (int i = 0; i < NX; ++i) t.P[i * NX + i] = p0[i];
+  t.id = id; t.tsu = 0; t.hits = 0; t.hit_streak = 0; t.age = 0;
+  t.conf = det[4]; t.cls = det[5];
+  t.has_last = 0; t.has_vel = 0; t.observed = 0; t.has_frozen = 0; t.missed = 0; t.n_obs = 0;
+  for (int i = 0; i < 5; ++i) t.last_obs[i] = -1.0;
+  for (int i = 0; i < 4; ++i) t.obs_age[i] = -1;
+  t.vel[0] = t.vel[1] = 0.0;
+  for (int i = 0; i < NZ; ++i) t.prev_z[i] = 0.0;
+}
+
+__device__ __forceinline__ double iou_of(const double* a, const double* b) {
+  double w = fmax(0.0, fmin(a[2], b[2]) - fmax(a[0], b[0]));
+  double h = fmax(0.0, fmin(a[3], b[3]) - fmax(a[1], b[1]));
+  double wh = w * h;
+  return wh / ((a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - wh);
+}
+
+__device__ __forceinline__ double diou_of(const double* a, const double* b) {
+  double iou = iou_of(a, b);
+  double cxa = (a[0] + a[2]) / 2.0, cya = (a[1] + a[3]) / 2.0;
+  double cxb = (b[0] + b[2]) / 2.0, cyb = (b[1] + b[3]) / 2.0;
+  double ex = cxa - cxb, ey = cya - cyb;
+  double inner = ex * ex + ey * ey;
+  double ox = fmax(a[2], b[2]) - fmin(a[0], b[0]);
+  double oy = fmax(a[3], b[3]) - fmin(a[1], b[1]);
+  double outer = ox * ox + oy * oy;
+  return (iou - inner / outer + 1) / 2.0;
+}
+
+// Rectangular min-cost assignment, same procedure and tie rule as
+// oracle/ocsort.py:assign_min_cost.  cost is [n][ld] (row-major, m used columns).
+// Writes row_of_col[j] (-1 = free) for the ORIGINAL orientation via out_row/out_col pairs.
+__device__ int assign_min_cost(const double* cost, int ld, int n, int m, int* pair_r,
+                               int* pair_c) {
+  if (n == 0 || m == 0) return 0;
+  const bool tr = n > m;
+  const int N = tr ? m : n, M = tr ? n : m;
+  double u[kMaxT + 1], v[kMaxT + 1], minv[kMaxT + 1];
+  int p[kMaxT + 1], way[kMaxT + 1];
+  bool used[kMaxT + 1];
+  for (int j = 0; j <= M; ++j) { v[j] = 0.0; p[j] = 0; way[j] = 0; }
+  for (int i = 0; i <= N; ++i) u[i] = 0.0;
+  for (int i = 1; i <= N; ++i) {
+    p[0] = i;
+    int j0 = 0;
+    for (int j = 0; j <= M; ++j) { minv[j] = INFINITY; used[j] = false; }
+    while (true) {
+      used[j0] = true;
+      int i0 = p[j0], j1 = 0;
+      double delta = INFINITY;
+      for (int j = 1; j <= M; ++j) {
+        if (used[j]) continue;
+        double cij = tr ? cost[(j - 1) * ld + (i0 - 1)] : cost[(i0 - 1) * ld + (j - 1)];
+        double cur = cij - u[i0] - v[j];
+        if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
+        if (minv[j] < delta) { delta = minv[j]; j1 = j; }
+      }
+      for (int j = 0; j <= M; ++j) {
+        if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
+        else minv[j] -= delta;
+      }
+      j0 = j1;
+      if (p[j0] == 0) break;
+    }
+    while (true) {
+      int j1 = way[j0];
+      p[j0] = p[j1];
+      j0 = j1;
+      if (j0 == 0) break;
+    }
+  }
+  // emit pairs sorted by row (row = first index of the original orientation)
+  int cnt = 0;
+  if (!tr) {
+    for (int i = 1; i <= N; ++i)
+      for (int j = 1; j <= M; ++j)
+        if (p[j] == i) { pair_r[cnt] = i - 1; pair_c[cnt] = j - 1; ++cnt; }
+  } else {
+    for (int j = 1; j <= M; ++j)
+      if (p[j] != 0) { pair_r[cnt] = j - 1; pair_c[cnt] = p[j] - 1; ++cnt; }
+  }
+  return cnt;
+}
+
+struct Shared {
+  double dets[kMaxD][6];
+  double tbox[kMaxT][4];        // predicted boxes, list order
+  double iou[kMaxD][kMaxT];
+  double cost[kMaxD][kMaxT];
+  int pair_d[kMaxD], pair_t[kMaxD];
+  int un_d[kMaxD * 2], un_t[kMaxT * 2];
+  int n_pairs, n_un_d, n_un_t, nd, nt, go;
+  unsigned char nanflag[kMaxT];
+};
+
+__global__ void __launch_bounds__(32) tracker_update_kernel(
+    Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
+    const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det,
+    double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count) {
+  __shared__ Shared sh;
+  const int v = blockIdx.x, lane = threadIdx.x;
+  Video& vid = videos[v];
+  Trk* trk = tracks + (size_t)v * kMaxT;
+  const int nf = min(n_frames[v], F);
+  const double vfps = fps[v];
+  double* vrows = rows + (size_t)v * row_cap * VBT_ROW_COLS;
+
+  for (int f = 0; f < nf; ++f) {
+    const int nd0 = det_count[(size_t)v * F + f];
+    if (nd0 <= 0) continue;                         // track.py:180-181
+    const double* fd = dets + ((size_t)v * F + f) * max_det * 6;
+    if (lane == 0) {
+      vid.frame_count += 1;
+      int nd = 0;
+      for (int i = 0; i < nd0 && i < max_det; ++i) {
+        if (fd[i * 6 + 4] > prm.det_thresh) {
+          if (nd >= kMaxD) { vid.status = VBT_ECAPACITY; break; }
+          for (int j = 0; j < 6; ++j) sh.dets[nd][j] = fd[i * 6 + j];
+          ++nd;
+        }
+      }
+      sh.nd = nd;
+      sh.nt = vid.n_tracks;
+    }
+    __syncwarp();
+    // ---- predict every track (lane-parallel) ---------------------------------------
+    for (int t = lane; t < sh.nt; t += 32) {
+      double b[4];
+      trk_predict(trk[vid.order[t]], b);
+      for (int j = 0; j < 4; ++j) sh.tbox[t][j] = b[j];
+      sh.nanflag[t] = (isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3])) ? 1 : 0;
+    }
+    __syncwarp();
+    if (lane == 0) {                                // drop NaN tracks, keep list order
+      int k = 0;
+      for (int t = 0; t < sh.nt; ++t) {
+        int slot = vid.order[t];
+        if (sh.nanflag[t]) { vid.used[slot] = 0; continue; }
+        vid.order[k] = slot;
+        for (int j = 0; j < 4; ++j) sh.tbox[k][j] = sh.tbox[t][j];
+        ++k;
+      }
+      sh.nt = vid.n_tracks = k;
+    }
+    __syncwarp();
+    const int nd = sh.nd, nt = sh.nt;
+    // ---- first association round ----------------------------------------------------
+    for (int i = lane; i < nd * nt; i += 32) {
+      int d = i / nt, t = i % nt;
+      sh.iou[d][t] = iou_of(sh.dets[d], sh.tbox[t]);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      sh.n_pairs = 0;
+      sh.go = 0;                                    // 1: Hungarian needed
+      if (nt > 0 && nd > 0) {
+        int rmax = 0, cmax = 0;
+        for (int d = 0; d < nd; ++d) {
+          int c = 0;
+          for (int t = 0; t < nt; ++t) c += sh.iou[d][t] > prm.iou_threshold;
+          rmax = max(rmax, c);
+        }
+        for (int t = 0; t < nt; ++t) {
+          int c = 0;
+          for (int d = 0; d < nd; ++d) c += sh.iou[d][t] > prm.iou_threshold;
+          cmax = max(cmax, c);
+        }
+        if (rmax == 1 && cmax == 1) {
+          for (int d = 0; d < nd; ++d)
+            for (int t = 0; t < nt; ++t)
+              if (sh.iou[d][t] > prm.iou_threshold) {
+                sh.pair_d[sh.n_pairs] = d; sh.pair_t[sh.n_pairs] = t; ++sh.n_pairs;
+              }
+        } else {
+          sh.go = 1;
+        }
+      }
+    }
+    __syncwarp();
+    if (sh.go) {
+      const double kPi = 3.141592653589793;
+      for (int i = lane; i < nd * nt; i += 32) {
+        int d = i / nt, t = i % nt;
+        const Trk& tk = trk[vid.order[t]];
+        const double* prev = k_previous(tk, prm.delta_t);
+        double pb[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
+        if (prev) for (int j = 0; j < 5; ++j) pb[j] = prev[j];
+        double cxd = (sh.dets[d][0] + sh.dets[d][2]) / 2.0, cyd = (sh.dets[d][1] + sh.dets[d][3]) / 2.0;
+        double cxp = (pb[0] + pb[2]) / 2.0, cyp = (pb[1] + pb[3]) / 2.0;
+        double ddx = cxd - cxp, ddy = cyd - cyp;
+        double norm = sqrt(ddx * ddx + ddy * ddy) + 1e-6;
+        ddx = ddx / norm; ddy = ddy / norm;
+        double vy = tk.has_vel ? tk.vel[0] : 0.0, vx = tk.has_vel ? tk.vel[1] : 0.0;
+        double c = vx * ddx + vy * ddy;
+        c = fmin(fmax(c, -1.0), 1.0);
+        double ang = (kPi / 2.0 - fabs(acos(c))) / kPi;
+        double valid = (pb[4] >= 0) ? 1.0 : 0.0;
+        double mult = prm.vdc_cls ? sh.dets[d][5] : sh.dets[d][4];
+        double angle_cost = ((valid * ang) * prm.inertia) * mult;
+        sh.cost[d][t] = -(sh.iou[d][t] + angle_cost);
+      }
+      __syncwarp();
+      if (lane == 0)
+        sh.n_pairs = assign_min_cost(&sh.cost[0][0], kMaxT, nd, nt, sh.pair_d, sh.pair_t);
+      __syncwarp();
+    }
+    if (lane == 0) {       // unmatched lists + low-IoU rejection, upstream order
+      bool md[kMaxD], mt[kMaxT];
+      for (int d = 0; d < nd; ++d) md[d] = false;
+      for (int t = 0; t < nt; ++t) mt[t] = false;
+      for (int i = 0; i < sh.n_pairs; ++i) { md[sh.pair_d[i]] = true; mt[sh.pair_t[i]] = true; }
+      int nud = 0, nut = 0, k = 0;
+      for (int d = 0; d < nd; ++d) if (!md[d]) sh.un_d[nud++] = d;
+      for (int t = 0; t < nt; ++t) if (!mt[t]) sh.un_t[nut++] = t;
+      for (int i = 0; i < sh.n_pairs; ++i) {
+        int d = sh.pair_d[i], t = sh.pair_t[i];
+        if (sh.iou[d][t] < prm.iou_threshold) { sh.un_d[nud++] = d; sh.un_t[nut++] = t; }
+        else { sh.pair_d[k] = d; sh.pair_t[k] = t; ++k; }
+      }
+      sh.n_pairs = k; sh.n_un_d = nud; sh.n_un_t = nut;
+    }
+    __syncwarp();
+    for (int i = lane; i < sh.n_pairs; i += 32)
+      trk_update(trk[vid.order[sh.pair_t[i]]], sh.dets[sh.pair_d[i]], prm.delta_t);
+    __syncwarp();
+    // ---- second round: unmatched detections vs last observations (DIoU) --------------
+    if (sh.n_un_d > 0 && sh.n_un_t > 0) {
+      const int a_n = sh.n_un_d, b_n = sh.n_un_t;
+      for (int i = lane; i < a_n * b_n; i += 32) {
+        int a = i / b_n, b = i % b_n;
+        const Trk& tk = trk[vid.order[sh.un_t[b]]];
+        sh.cost[a][b] = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
+      }
+      __syncwarp();
+      if (lane == 0) {
+        double mx = -INFINITY;
+        bool any_nan = false;
+        for (int a = 0; a < a_n; ++a)
+          for (int b = 0; b < b_n; ++b) {
+            double q = sh.cost[a][b];
+            if (isnan(q)) any_nan = true; else mx = fmax(mx, q);
+          }
+        sh.n_pairs = 0;
+        if (!any_nan && mx > prm.iou_threshold) {
+          for (int a = 0; a < a_n; ++a)
+            for (int b = 0; b < b_n; ++b) sh.iou[a][b] = -sh.cost[a][b];
+          int pr[kMaxD], pc[kMaxD];
+          int np = assign_min_cost(&sh.iou[0][0], kMaxT, a_n, b_n, pr, pc);
+          bool rm_d[kMaxD * 2], rm_t[kMaxT * 2];
+          for (int a = 0; a < a_n; ++a) rm_d[a] = false;
+          for (int b = 0; b < b_n; ++b) rm_t[b] = false;
+          int k = 0;
+          for (int i = 0; i < np; ++i) {
+            if (sh.cost[pr[i]][pc[i]] < prm.iou_threshold) continue;
+            sh.pair_d[k] = sh.un_d[pr[i]]; sh.pair_t[k] = sh.un_t[pc[i]]; ++k;
+            rm_d[pr[i]] = true; rm_t[pc[i]] = true;
+          }
+          sh.n_pairs = k;
+          // np.setdiff1d: sorted unique remainder
+          int nud = 0, nut = 0;
+          bool keep_d[kMaxD], keep_t[kMaxT];
+          for (int d = 0; d < nd; ++d) keep_d[d] = false;
+          for (int t = 0; t < nt; ++t) keep_t[t] = false;
+          for (int a = 0; a < a_n; ++a) if (!rm_d[a]) keep_d[sh.un_d[a]] = true;
+          for (int b = 0; b < b_n; ++b) if (!rm_t[b]) keep_t[sh.un_t[b]] = true;
+          for (int d = 0; d < nd; ++d) if (keep_d[d]) sh.un_d[nud++] = d;
+          for (int t = 0; t < nt; ++t) if (keep_t[t]) sh.un_t[nut++] = t;
+          sh.n_un_d = nud; sh.n_un_t = nut;
+        }
+      }
+      __syncwarp();
+      for (int i = lane; i < sh.n_pairs; i += 32)
+        trk_update(trk[vid.order[sh.pair_t[i]]], sh.dets[sh.pair_d[i]], prm.delta_t);
+      __syncwarp();
+    }
+    for (int i = lane; i < sh.n_un_t; i += 32)
+      trk_update(trk[vid.order[sh.un_t[i]]], nullptr, prm.delta_t);
+    __syncwarp();
+    // ---- births, output rows, deaths (lane 0, list order matters) ---------------------
+    if (lane == 0) {
+      for (int i = 0; i < sh.n_un_d; ++i) {
+        int slot = -1;
+        for (int s = 0; s < kMaxT; ++s) if (!vid.used[s]) { slot = s; break; }
+        if (slot < 0 || vid.n_tracks >= kMaxT) { vid.status = VBT_ECAPACITY; break; }
+        vid.used[slot] = 1;
+        trk_init(trk[slot], sh.dets[sh.un_d[i]], vid.next_id++);
+        vid.order[vid.n_tracks++] = slot;
+      }
+      const double time = (double)frame_no[(size_t)v * F + f] / vfps;     // track.py:169
+      const bool last_frame = (f == nf - 1);
+      int n_out = 0;
+      int rc = row_count[v];
+      for (int t = vid.n_tracks - 1; t >= 0; --t) {
+        Trk& tk = trk[vid.order[t]];
+        double box[4];
+        double sum = tk.last_obs[0] + tk.last_obs[1] + tk.last_obs[2] + tk.last_obs[3] + tk.last_obs[4];
+        if (!tk.has_last || sum < 0) x_to_box(tk.x, box);
+        else for (int j = 0; j < 4; ++j) box[j] = tk.last_obs[j];
+        if (tk.tsu < 1 && (tk.hit_streak >= prm.min_hits || vid.frame_count <= prm.min_hits)) {
+          if (rc >= row_cap) {
+            vid.status = VBT_ECAPACITY;
+          } else {
+            double* r = vrows + (size_t)rc * VBT_ROW_COLS;
+            r[0] = (double)(tk.id + 1);
+            r[1] = time;
+            r[2] = (box[0] + box[2]) / 2;          // odt.py:43-50
+            r[3] = (box[1] + box[3]) / 2;
+            r[4] = tk.x[4];                        // track.py:199
+            r[5] = tk.x[5];
+            r[6] = fabs(box[3] - box[1]);          // odt.py:32-40
+            r[7] = fabs(box[2] - box[0]);          // odt.py:22-29
+            ++rc;
+          }
+          if (last_out && last_frame && n_out < max_det) {
+            double* o = last_out + ((size_t)v * max_det + n_out) * 9;
+            o[0] = box[0]; o[1] = box[1]; o[2] = box[2]; o[3] = box[3];
+            o[4] = (double)(tk.id + 1); o[5] = tk.cls; o[6] = tk.conf; o[7] = tk.x[4]; o[8] = tk.x[5];
+          }
+          ++n_out;
+        }
+      }
+      row_count[v] = rc;
+      if (last_out_count && last_frame) last_out_count[v] = min(n_out, max_det);
+      int k = 0;
+      for (int t = 0; t < vid.n_tracks; ++t) {
+        int slot = vid.order[t];
+        if (trk[slot].tsu > prm.max_age) { vid.used[slot] = 0; continue; }
+        vid.order[k++] = slot;
+      }
+      vid.n_tracks = k;
+    }
+    __syncwarp();
+  }
+  // a call whose last frame was empty still reports "nothing emitted"
+  if (lane == 0 && last_out_count && nf > 0 && det_count[(size_t)v * F + nf - 1] <= 0)
+    last_out_count[v] = 0;
+}
+
+__global__ void tracker_reset_kernel(Video* videos, int V) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  Video& vid = videos[v];
+  vid.frame_count = vid.next_id = vid.n_tracks = vid.status = 0;
+  for (int i = 0; i < kMaxT; ++i) { vid.order[i] = 0; vid.used[i] = 0; }
+}
+
+__global__ void tracker_peek_kernel(const Video* videos, const Trk* tracks, int v, double* out,
+                                    int32_t* out_n) {
+  if (blockIdx.x || threadIdx.x) return;
+  const Video& vid = videos[v];
+  for (int t = 0; t < vid.n_tracks; ++t) {
+    const Trk& tk = tracks[(size_t)v * kMaxT + vid.order[t]];
+    for (int j = 0; j < NX; ++j) out[t * 9 + j] = tk.x[j];
+    out[t * 9 + 7] = (double)tk.id;
+    out[t * 9 + 8] = (double)tk.tsu;
+  }
+  *out_n = vid.n_tracks;
+}
+
+__global__ void tracker_status_kernel(const Video* videos, int V, int32_t* out) {
+  int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < V) out[v] = videos[v].status;
+}
+
+}  // namespace
+
+struct vbt_tracker {
+  int V, max_tracks;
+  Params prm;
+  Video* videos;
+  Trk* tracks;
+  double* peek;      // [kMaxT*9 + 1]
+  int32_t* scratch;  // [max(V,1)]
+};
+
+extern "C" {
+
+int vbt_tracker_create(int V, int max_tracks, const vbt_tracker_params* p, vbt_tracker** out) {
+  VBT_REQUIRE(out && p && V > 0, "vbt_tracker_create: bad arguments");
+  VBT_REQUIRE(max_tracks > 0 && max_tracks <= kMaxT, "vbt_tracker_create: max_tracks must be 1..%d",
+              kMaxT);
+  VBT_REQUIRE(p->delta_t >= 1 && p->delta_t <= 3, "vbt_tracker_create: delta_t must be 1..3");
+  if (int rc = vbt::ensure_device()) return rc;
+  vbt_tracker* t = new vbt_tracker();
+  t->V = V; t->max_tracks = max_tracks;
+  t->prm.det_thresh = p->det_thresh; t->prm.iou_threshold = p->iou_threshold;
+  t->prm.inertia = p->inertia; t->prm.max_age = p->max_age; t->prm.min_hits = p->min_hits;
+  t->prm.delta_t = p->delta_t; t->prm.vdc_cls = p->vdc_uses_class_column;
+  VBT_CHECK_CUDA(cudaMalloc(&t->videos, sizeof(Video) * (size_t)V));
+  VBT_CHECK_CUDA(cudaMalloc(&t->tracks, sizeof(Trk) * (size_t)V * kMaxT));
+  VBT_CHECK_CUDA(cudaMalloc(&t->peek, sizeof(double) * (kMaxT * 9)));
+  VBT_CHECK_CUDA(cudaMalloc(&t->scratch, sizeof(int32_t) * (size_t)(V + 1)));
+  *out = t;
+  return vbt_tracker_reset(t, nullptr);
+}
+
+void vbt_tracker_destroy(vbt_tracker* t) {
+  if (!t) return;
+  cudaFree(t->videos); cudaFree(t->tracks); cudaFree(t->peek); cudaFree(t->scratch);
+  delete t;
+}
+
+int vbt_tracker_reset(vbt_tracker* t, void* stream) {
+  VBT_REQUIRE(t, "vbt_tracker_reset: null handle");
+  tracker_reset_kernel<<<vbt::ceil_div(t->V, 64), 64, 0, (cudaStream_t)stream>>>(t->videos, t->V);
+  VBT_LAUNCHED(1);
+  return VBT_OK;
+}
+
+int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* dev_det_count,
+                       const int32_t* dev_frame_no, const double* dev_fps,
+                       const int32_t* dev_n_frames, int F, int max_det, double* dev_rows,
+                       int32_t* dev_row_count, int row_cap, double* dev_last_out,
+                       int32_t* dev_last_out_count, void* stream) {
+  VBT_REQUIRE(t && dev_dets && dev_det_count && dev_frame_no && dev_fps && dev_n_frames &&
+                  dev_rows && dev_row_count, "vbt_tracker_update: null pointer");
+  VBT_REQUIRE(F > 0 && max_det > 0 && max_det <= kMaxD && row_cap > 0,
+              "vbt_tracker_update: F=%d max_det=%d (<=%d) row_cap=%d", F, max_det, kMaxD, row_cap);
+  tracker_update_kernel<<<t->V, 32, 0, (cudaStream_t)stream>>>(
+      t->videos, t->tracks, t->prm, dev_dets, dev_det_count, dev_frame_no, dev_fps, dev_n_frames,
+      F, max_det, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count);
+  VBT_LAUNCHED(1);
+  return VBT_OK;
+}
+
+int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream) {
+  VBT_REQUIRE(t && host_status, "vbt_tracker_status: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  tracker_status_kernel<<<vbt::ceil_div(t->V, 64), 64, 0, st>>>(t->videos, t->V, t->scratch);
+  VBT_LAUNCHED(1);
+  VBT_CHECK_CUDA(cudaMemcpyAsync(host_status, t->scratch, sizeof(int32_t) * (size_t)t->V,
+                                 cudaMemcpyDeviceToHost, st));
+  VBT_CHECK_CUDA(cudaStreamSynchronize(st));
+  for (int v = 0; v < t->V; ++v)
+    if (host_status[v] != 0) {
+      vbt::set_error("tracker video %d overflowed (more than %d live tracks, %d detections per "
+                     "frame, or the row table)", v, kMaxT, kMaxD);
+      return VBT_ECAPACITY;
+    }
+  return VBT_OK;
+}
+
+int vbt_tracker_peek(vbt_tracker* t, int v, double* host_tracks, void* stream) {
+  VBT_REQUIRE(t && host_tracks && v >= 0 && v < t->V, "vbt_tracker_peek: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  tracker_peek_kernel<<<1, 1, 0, st>>>(t->videos, t->tracks, v, t->peek, t->scratch + t->V);
+  VBT_LAUNCHED(1);
+  int32_t n = 0;
+  VBT_CHECK_CUDA(cudaMemcpyAsync(&n, t->scratch + t->V, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  VBT_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (n > 0)
+    VBT_CHECK_CUDA(cudaMemcpy(host_tracks, t->peek, sizeof(double) * 9 * (size_t)n,
+                              cudaMemcpyDeviceToHost));
+  return n;
+}
+
+}  // extern "C"
