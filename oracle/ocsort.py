@@ -253,6 +253,8 @@ def assign_min_cost(cost):
                     if minv[j] < delta:
                         delta = minv[j]
                         j1 = j
+            if j1 == 0:
+                raise ValueError('assignment cost matrix holds NaN/inf')
             for j in range(m + 1):
                 if used[j]:
                     u[p[j]] += delta

@@ -12,6 +12,8 @@ Writes
   classes (plot.analyze_df -> VelocityTracker/RunningAverage/Phase) produce on the
   plot.py-smoothed series, float64 [k,6] t_start,t_end,y_start,y_end,rom,type; plus the
   same for qualysis_dfs/ as extra known-answer inputs,
+* tests/golden/eval_detections_stats.json -- shape statistics of dfs/eval_detections.pkl.gz
+  (25 detections per image, 1/256 score grid, score-descending blocks),
 * tests/golden/figs_ocsort_labels.json -- the ROM / ACV text labels (2 decimals,
   plot.py:178,186) pulled out of figs_ocsort/*.pdf by inflating the PDF streams.
 
@@ -91,6 +93,19 @@ def main():
                         columns=['id']).to_numpy(dtype=np.float64)
     for p in sorted(glob.glob(os.path.join(REF, 'figs_ocsort', '*.pdf'))):
         labels[os.path.basename(p)[:-4]] = pdf_labels(p)
+    # detector known-answer STATISTICS (the per-image detections need the absent .tflite
+    # weights to reproduce; what the post-process oracle can be held to is their shape)
+    ev = pd.read_pickle(os.path.join(REF, 'dfs', 'eval_detections.pkl.gz'))
+    sc = ev['Score'].to_numpy().reshape(-1, 25)
+    stats = {
+        'rows': int(len(ev)), 'models': sorted(ev['Model'].unique().tolist()),
+        'detections_per_image': 25, 'images_per_model': int(len(ev) // 25 // 6),
+        'scores_on_1_256_grid': bool(np.all(sc * 256 == np.round(sc * 256))),
+        'blocks_score_descending': bool(np.all(np.diff(sc, axis=1) <= 0)),
+        'min_score': float(sc.min()), 'max_score': float(sc.max()),
+    }
+    with open(os.path.join(HERE, 'eval_detections_stats.json'), 'w') as f:
+        json.dump(stats, f, indent=1, sort_keys=True)
     np.savez_compressed(os.path.join(HERE, 'dfs_ocsort.npz'), **tables)
     np.savez_compressed(os.path.join(HERE, 'velocity_phases.npz'), **phases)
     with open(os.path.join(HERE, 'figs_ocsort_labels.json'), 'w') as f:

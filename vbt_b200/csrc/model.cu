@@ -49,7 +49,8 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
     return VBT_EFORMAT;
   }
   for (const OpRecord& op : m->ops) {
-    bool ok = op.out >= 0 && op.out < hdr.n_tensors + 2 && op.n_in >= 1 && op.n_in <= 3;
+    bool ok = ((op.out >= 0 && op.out < hdr.n_tensors) || (op.out == -1 && op.out_kind != 0)) &&
+              op.n_in >= 1 && op.n_in <= 3;
     for (int i = 0; i < op.n_in && ok; ++i) ok = op.in[i] >= -1 && op.in[i] < hdr.n_tensors;
     if (!ok) {
       delete m;

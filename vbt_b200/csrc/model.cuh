@@ -29,8 +29,9 @@ struct BlobHeader {
   float box_scale;              // dequantisation of the raw box output
   int32_t box_zp;
   int32_t in_zp;                // uint8 input zero point (127)
-  int32_t reserved[7];
+  int32_t reserved[11];
 };
+static_assert(sizeof(BlobHeader) == 128, "blob header layout");
 
 enum OpType : int32_t {
   OP_STEM = 1,      // 3x3 s2 conv on the uint8 input, ReLU6
@@ -57,6 +58,7 @@ struct OpRecord {
   int32_t act_lo, act_hi;  // clamp of the int8 result
   int32_t pad_top, pad_left;
   int64_t w_off, bias_off, scale_off, lut_off;   // data-section byte offsets (-1 none)
+  int64_t out_elem_offset; // within-frame element offset (level offset for the heads)
   // OP_ADD / fused residual: integer rescale  out = clamp(((sum_i (x_i - zp_i)*mult_i)
   //                                             + round) >> shift) + zp_out)
   int32_t add_mult[3];
@@ -67,14 +69,15 @@ struct OpRecord {
   //   out_off(b) + p * out_pix_stride ; out_off(b) = tensor base + b * out_batch_stride
   int32_t out_kind;        // 0 workspace tensor, 1 raw class output, 2 raw box output
   int32_t out_pix_stride;
-  int64_t out_elem_offset; // within-frame element offset (level offset for the heads)
-  int32_t reserved[6];
+  int32_t reserved[7];
 };
+static_assert(sizeof(OpRecord) == 224, "op record layout");
 
 struct TensorRecord {
   int64_t ws_offset;   // per-frame byte offset inside the workspace
   int32_t h, w, c, c_p;
 };
+static_assert(sizeof(TensorRecord) == 24, "tensor record layout");
 
 }  // namespace vbt
 

@@ -1,0 +1,450 @@
+// K2-K5 -- the EfficientDet-Lite network as int8 kernels over NHWC activations.
+//
+// replaces: the graph inside tflite_runtime's signature_fn(images=...) (odt.py:58-61):
+// EfficientNet-Lite backbone (MBConv: 1x1 expand -> depthwise 3x3/5x5 -> 1x1 project
+// [+ residual]), BiFPN (quantised sum fusion with nearest-up / max-pool-down resampling
+// -> depthwise 3x3 -> 1x1) and the class / box heads, int8 per-tensor activations,
+// per-channel weights, int32 accumulate, fp32 requantisation, fused ReLU6 clamps, the
+// int8 LOGISTIC on the class output folded into the last conv's epilogue as a LUT.
+//
+// Data layout in HBM: every activation is [B, H, W, Cp] int8 with Cp = channels rounded
+// up to 16 (pad channels hold the tensor's zero point and meet zero weights), so every
+// pixel is a whole number of 128-bit words and a 1x1 conv is a K-major GEMM
+// [B*H*W, Cin_p] x [Cout_p, Cin_p]^T.  Tensor t of the layer program lives at
+// workspace + B * ws_offset[t].
+//
+// This file holds the SIMT kernels (stem, depthwise, fusion, pooling, and a dp4a
+// pointwise kernel used for shapes the tcgen05 GEMM in pw_umma.cu does not take).
+#include "model.cuh"
+
+namespace vbt {
+int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res,
+                   int8_t* out, long long out_batch_stride, int B, cudaStream_t st, bool* taken);
+}
+
+namespace {
+
+using vbt::OpRecord;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+__device__ __forceinline__ int requant(int acc, float mult, int zp, int lo, int hi) {
+  return clampi(__float2int_rn(__fmul_rn(__int2float_rn(acc), mult)) + zp, lo, hi);
+}
+
+__device__ __forceinline__ int s8(uint32_t word, int i) {
+  return (int)(int8_t)(word >> (8 * i));
+}
+
+// ---------------------------------------------------------------------------------------
+// stem: 3x3 stride-2 conv on the uint8 frame, 3 -> 32 channels, ReLU6 clamp
+// ---------------------------------------------------------------------------------------
+struct StemArgs {
+  const uint8_t* in; int8_t* out;
+  const int8_t* w; const int32_t* bias; const float* mult;   // w [cout_p][28]
+  int B, H, W, Ho, Wo, cout_p, pad_top, pad_left, zp_in, zp_out, lo, hi;
+};
+
+__global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
+  __shared__ int8_t sw[64 * 28];
+  __shared__ int32_t sb[64];
+  __shared__ float sm[64];
+  for (int i = threadIdx.x; i < a.cout_p * 28; i += blockDim.x) sw[i] = a.w[i];
+  for (int i = threadIdx.x; i < a.cout_p; i += blockDim.x) { sb[i] = a.bias[i]; sm[i] = a.mult[i]; }
+  __syncthreads();
+  const long long total = (long long)a.B * a.Ho * a.Wo;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
+       p += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(p % a.Wo), oy = (int)((p / a.Wo) % a.Ho), b = (int)(p / ((long long)a.Wo * a.Ho));
+    int x[27];
+    const uint8_t* fin = a.in + (size_t)b * a.H * a.W * 3;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = oy * 2 - a.pad_top + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = ox * 2 - a.pad_left + kx;
+        const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
+        const uint8_t* px = fin + ((size_t)iy * a.W + ix) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = in ? (int)__ldg(px + c) : a.zp_in;
+      }
+    }
+    int8_t* o = a.out + (size_t)p * a.cout_p;
+    for (int c0 = 0; c0 < a.cout_p; c0 += 16) {
+      uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int c = c0 + j;
+        int acc = sb[c];
+#pragma unroll
+        for (int t = 0; t < 27; ++t) acc += x[t] * (int)sw[c * 28 + t];
+        const int y = requant(acc, sm[c], a.zp_out, a.lo, a.hi);
+        packed[j >> 2] |= (uint32_t)(y & 0xff) << (8 * (j & 3));
+      }
+      *reinterpret_cast<uint4*>(o + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// depthwise kxk (k = 3 or 5, stride 1 or 2, TF-SAME): one thread = one output pixel x 16
+// channels (one 128-bit load per tap)
+// ---------------------------------------------------------------------------------------
+struct DwArgs {
+  const int8_t* in; int8_t* out;
+  const int8_t* w; const int32_t* bias; const float* mult;   // w [k*k][c_p]
+  int B, H, W, Ho, Wo, c_p, k, stride, pad_top, pad_left, zp_in, zp_out, lo, hi;
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
+  const int groups = a.c_p >> 4;
+  const long long total = (long long)a.B * a.Ho * a.Wo * groups;
+  const uint32_t zpw = (uint32_t)(a.zp_in & 0xff) * 0x01010101u;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long p = i / groups;
+    const int ox = (int)(p % a.Wo), oy = (int)((p / a.Wo) % a.Ho), b = (int)(p / ((long long)a.Wo * a.Ho));
+    const int c0 = gidx << 4;
+    int acc[16];
+    {
+      const int4* bp = reinterpret_cast<const int4*>(a.bias + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int4 v = __ldg(bp + q);
+        acc[q * 4 + 0] = v.x; acc[q * 4 + 1] = v.y; acc[q * 4 + 2] = v.z; acc[q * 4 + 3] = v.w;
+      }
+    }
+    const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.c_p + c0;
+#pragma unroll
+    for (int ky = 0; ky < K; ++ky) {
+      const int iy = oy * a.stride - a.pad_top + ky;
+#pragma unroll
+      for (int kx = 0; kx < K; ++kx) {
+        const int ix = ox * a.stride - a.pad_left + kx;
+        uint4 xv = make_uint4(zpw, zpw, zpw, zpw);
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
+          xv = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.c_p));
+        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(a.w + (size_t)(ky * K + kx) * a.c_p + c0));
+        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+        const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[q * 4 + j] += s8(xs[q], j) * s8(ws[q], j);
+      }
+    }
+    uint32_t packed[4] = {0, 0, 0, 0};
+    const float4* mp = reinterpret_cast<const float4*>(a.mult + c0);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float4 mv = __ldg(mp + q);
+      const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int y = requant(acc[q * 4 + j], ms[j], a.zp_out, a.lo, a.hi);
+        packed[q] |= (uint32_t)(y & 0xff) << (8 * j);
+      }
+    }
+    *reinterpret_cast<uint4*>(a.out + (size_t)p * a.c_p + c0) =
+        make_uint4(packed[0], packed[1], packed[2], packed[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// BiFPN fusion: quantised sum of up to 3 inputs, each optionally resampled to the node's
+// level (nearest-neighbour up, 3x3 stride-2 SAME max-pool down), ReLU6 clamp.
+// Also serves the stand-alone max-pool (n_in == 1, identity rescale skipped).
+// ---------------------------------------------------------------------------------------
+struct AddArgs {
+  const int8_t* in[3]; int8_t* out;
+  int n_in, B, Ho, Wo, c_p;
+  int in_h[3], in_w[3], resample[3], zp_in[3], mult[3];
+  int shift, zp_out, lo, hi, pool_only;
+};
+
+__device__ __forceinline__ uint4 fetch_resampled(const int8_t* base, int b, int oy, int ox, int Ho,
+                                                 int Wo, int ih, int iw, int mode, int c_p, int c0) {
+  const int8_t* fin = base + (size_t)b * ih * iw * c_p + c0;
+  if (mode == vbt::RS_NONE) {
+    return __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)oy * iw + ox) * c_p));
+  } else if (mode == vbt::RS_UP_NEAREST) {
+    const int sy = (oy * ih) / Ho, sx = (ox * iw) / Wo;
+    return __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)sy * iw + sx) * c_p));
+  }
+  // 3x3 stride-2 SAME max-pool: pad_before = total/2, out-of-range taps are skipped
+  const int pt = max((Ho - 1) * 2 + 3 - ih, 0) / 2, pl = max((Wo - 1) * 2 + 3 - iw, 0) / 2;
+  uint4 m = make_uint4(0x80808080u, 0x80808080u, 0x80808080u, 0x80808080u);
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int iy = oy * 2 - pt + ky;
+    if (iy < 0 || iy >= ih) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ox * 2 - pl + kx;
+      if (ix < 0 || ix >= iw) continue;
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * iw + ix) * c_p));
+      m.x = __vmaxs4(m.x, v.x); m.y = __vmaxs4(m.y, v.y);
+      m.z = __vmaxs4(m.z, v.z); m.w = __vmaxs4(m.w, v.w);
+    }
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256) add_kernel(AddArgs a) {
+  const int groups = a.c_p >> 4;
+  const long long total = (long long)a.B * a.Ho * a.Wo * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(i % groups);
+    const long long p = i / groups;
+    const int ox = (int)(p % a.Wo), oy = (int)((p / a.Wo) % a.Ho), b = (int)(p / ((long long)a.Wo * a.Ho));
+    const int c0 = gidx << 4;
+    uint4 o;
+    if (a.pool_only) {
+      o = fetch_resampled(a.in[0], b, oy, ox, a.Ho, a.Wo, a.in_h[0], a.in_w[0], vbt::RS_DOWN_MAXPOOL,
+                          a.c_p, c0);
+    } else {
+      int acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 1 << (a.shift - 1);
+      for (int n = 0; n < a.n_in; ++n) {
+        const uint4 v = fetch_resampled(a.in[n], b, oy, ox, a.Ho, a.Wo, a.in_h[n], a.in_w[n],
+                                        a.resample[n], a.c_p, c0);
+        const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[q * 4 + j] += (s8(xs[q], j) - a.zp_in[n]) * a.mult[n];
+      }
+      uint32_t packed[4] = {0, 0, 0, 0};
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int y = clampi((acc[j] >> a.shift) + a.zp_out, a.lo, a.hi);
+        packed[j >> 2] |= (uint32_t)(y & 0xff) << (8 * (j & 3));
+      }
+      o = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+    *reinterpret_cast<uint4*>(a.out + (size_t)p * a.c_p + c0) = o;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// pointwise 1x1 conv, SIMT dp4a GEMM: 64 pixels x 64 output channels per CTA, K chunks
+// of 64 bytes staged in shared memory; epilogue = requantise (+ quantised residual add)
+// (+ LOGISTIC LUT), written through shared memory as 128-bit rows when the output is a
+// padded workspace tensor, bytewise for the packed head outputs.
+// ---------------------------------------------------------------------------------------
+struct PwArgs {
+  const int8_t* in; const int8_t* res; int8_t* out;
+  const int8_t* w; const int32_t* bias; const float* mult; const int8_t* lut;
+  long long M;                // B * H * W
+  int HW, cin_p, cout, cout_p;
+  int zp_conv, lo, hi;        // requant target of the conv itself
+  int has_res, res_zp, add_mult0, add_mult1, add_shift, zp_final;
+  int out_pix_stride; long long out_batch_stride, out_elem_offset;
+  int vector_out;             // 1: out rows are 16-byte aligned multiples
+};
+
+constexpr int PW_BM = 64, PW_BN = 64, PW_BK = 64;
+
+__global__ void __launch_bounds__(256) pw_dp4a_kernel(PwArgs a) {
+  __shared__ int As[PW_BM][PW_BK / 4 + 1];
+  __shared__ int Ws[PW_BN][PW_BK / 4 + 1];
+  __shared__ __align__(16) int8_t Os[PW_BM][PW_BN];
+  const int tid = threadIdx.x;
+  const long long m0 = (long long)blockIdx.x * PW_BM;
+  const int n0 = blockIdx.y * PW_BN;
+  const int ty = tid >> 4, tx = tid & 15;     // rows ty*4..+3 ; cols tx + 16*j
+  int acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+
+  const int lrow = tid >> 2, lseg = tid & 3;  // loader: one 16-byte segment per thread
+  for (int k0 = 0; k0 < a.cin_p; k0 += PW_BK) {
+    int4 av = make_int4(0, 0, 0, 0), wv = make_int4(0, 0, 0, 0);
+    const int kk = k0 + lseg * 16;
+    if (kk < a.cin_p) {
+      if (m0 + lrow < a.M)
+        av = __ldg(reinterpret_cast<const int4*>(a.in + (size_t)(m0 + lrow) * a.cin_p + kk));
+      if (n0 + lrow < a.cout_p)
+        wv = __ldg(reinterpret_cast<const int4*>(a.w + (size_t)(n0 + lrow) * a.cin_p + kk));
+    }
+    __syncthreads();
+    As[lrow][lseg * 4 + 0] = av.x; As[lrow][lseg * 4 + 1] = av.y;
+    As[lrow][lseg * 4 + 2] = av.z; As[lrow][lseg * 4 + 3] = av.w;
+    Ws[lrow][lseg * 4 + 0] = wv.x; Ws[lrow][lseg * 4 + 1] = wv.y;
+    Ws[lrow][lseg * 4 + 2] = wv.z; Ws[lrow][lseg * 4 + 3] = wv.w;
+    __syncthreads();
+#pragma unroll
+    for (int kw = 0; kw < PW_BK / 4; ++kw) {
+      int av4[4], wv4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) av4[i] = As[ty * 4 + i][kw];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) wv4[j] = Ws[tx + 16 * j][kw];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = __dp4a(av4[i], wv4[j], acc[i][j]);
+    }
+  }
+  // epilogue
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int n = n0 + tx + 16 * j;
+    const bool nvalid = n < a.cout_p;
+    const int bias = nvalid ? __ldg(a.bias + n) : 0;
+    const float mult = nvalid ? __ldg(a.mult + n) : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long m = m0 + ty * 4 + i;
+      int y = requant(acc[i][j] + bias, mult, a.zp_conv, a.has_res ? -128 : a.lo, a.has_res ? 127 : a.hi);
+      if (a.has_res && nvalid && m < a.M) {
+        const int r = (int)a.res[(size_t)m * a.cout_p + n];
+        const int s = (y - a.zp_conv) * a.add_mult0 + (r - a.res_zp) * a.add_mult1 +
+                      (1 << (a.add_shift - 1));
+        y = clampi((s >> a.add_shift) + a.zp_final, a.lo, a.hi);
+      }
+      if (a.lut) y = (int)a.lut[y + 128];
+      Os[ty * 4 + i][tx + 16 * j] = (int8_t)y;
+    }
+  }
+  __syncthreads();
+  if (a.vector_out) {
+    const long long m = m0 + lrow;
+    const int n = n0 + lseg * 16;
+    if (m < a.M && n < a.cout_p) {
+      const long long b = m / a.HW, p = m % a.HW;
+      int8_t* dst = a.out + b * a.out_batch_stride + a.out_elem_offset + p * a.out_pix_stride + n;
+      *reinterpret_cast<int4*>(dst) = *reinterpret_cast<const int4*>(&Os[lrow][lseg * 16]);
+    }
+  } else {
+    for (int e = tid; e < PW_BM * PW_BN; e += 256) {
+      const int r = e / PW_BN, c = e % PW_BN;
+      const long long m = m0 + r;
+      const int n = n0 + c;
+      if (m < a.M && n < a.cout) {
+        const long long b = m / a.HW, p = m % a.HW;
+        a.out[b * a.out_batch_stride + a.out_elem_offset + p * a.out_pix_stride + n] = Os[r][c];
+      }
+    }
+  }
+}
+
+int grid_for(long long work_items, int threads) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace,
+                          size_t workspace_bytes, int8_t* dev_out_cls, int8_t* dev_out_box,
+                          void* stream) {
+  using namespace vbt;
+  VBT_REQUIRE(m && dev_in && dev_workspace && dev_out_cls && dev_out_box, "vbt_detect: null pointer");
+  VBT_REQUIRE(B > 0, "vbt_detect: B=%d", B);
+  VBT_REQUIRE(workspace_bytes >= (size_t)B * (size_t)m->hdr.ws_bytes_per_frame,
+              "vbt_detect: workspace of %zu bytes is smaller than B * %lld", workspace_bytes,
+              (long long)m->hdr.ws_bytes_per_frame);
+  VBT_REQUIRE(((uintptr_t)dev_workspace & 255) == 0, "vbt_detect: workspace must be 256-byte aligned");
+  VBT_REQUIRE(!m->ops.empty(), "vbt_detect: the model holds no layer program (anchors only)");
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* ws = static_cast<uint8_t*>(dev_workspace);
+  const long long Np = m->hdr.n_anchors_pad;
+  auto tensor_ptr = [&](int id) -> int8_t* {
+    return reinterpret_cast<int8_t*>(ws + (size_t)B * (size_t)m->tensors[id].ws_offset);
+  };
+  auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
+  int launched = 0;
+  for (const OpRecord& op : m->ops) {
+    switch (op.type) {
+      case OP_STEM: {
+        StemArgs a;
+        a.in = dev_in; a.out = tensor_ptr(op.out);
+        a.w = reinterpret_cast<const int8_t*>(data(op.w_off));
+        a.bias = reinterpret_cast<const int32_t*>(data(op.bias_off));
+        a.mult = reinterpret_cast<const float*>(data(op.scale_off));
+        a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out;
+        a.cout_p = op.cout_p; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
+        a.zp_in = op.zp_in[0]; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
+        VBT_REQUIRE(op.cout_p <= 64 && op.k == 3 && op.stride == 2, "vbt_detect: unsupported stem");
+        stem_kernel<<<grid_for((long long)B * op.h_out * op.w_out, 128), 128, 0, st>>>(a);
+        break;
+      }
+      case OP_DW: {
+        DwArgs a;
+        a.in = tensor_ptr(op.in[0]); a.out = tensor_ptr(op.out);
+        a.w = reinterpret_cast<const int8_t*>(data(op.w_off));
+        a.bias = reinterpret_cast<const int32_t*>(data(op.bias_off));
+        a.mult = reinterpret_cast<const float*>(data(op.scale_off));
+        a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out; a.c_p = op.cout_p;
+        a.k = op.k; a.stride = op.stride; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
+        a.zp_in = op.zp_in[0]; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
+        const int grid = grid_for((long long)B * op.h_out * op.w_out * (op.cout_p / 16), 256);
+        if (op.k == 3) dw_kernel<3><<<grid, 256, 0, st>>>(a);
+        else if (op.k == 5) dw_kernel<5><<<grid, 256, 0, st>>>(a);
+        else VBT_REQUIRE(false, "vbt_detect: depthwise kernel size %d", op.k);
+        break;
+      }
+      case OP_ADD:
+      case OP_MAXPOOL: {
+        AddArgs a;
+        a.n_in = op.n_in; a.B = B; a.Ho = op.h_out; a.Wo = op.w_out; a.c_p = op.cout_p;
+        for (int i = 0; i < 3; ++i) {
+          a.in[i] = (i < op.n_in) ? tensor_ptr(op.in[i]) : nullptr;
+          a.in_h[i] = op.in_h[i]; a.in_w[i] = op.in_w[i]; a.resample[i] = op.resample[i];
+          a.zp_in[i] = op.zp_in[i]; a.mult[i] = op.add_mult[i];
+        }
+        a.shift = op.add_shift; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
+        a.pool_only = (op.type == OP_MAXPOOL);
+        a.out = tensor_ptr(op.out);
+        add_kernel<<<grid_for((long long)B * op.h_out * op.w_out * (op.cout_p / 16), 256), 256, 0, st>>>(a);
+        break;
+      }
+      case OP_PW: {
+        const int8_t* in = tensor_ptr(op.in[0]);
+        const int8_t* res = (op.n_in == 2) ? tensor_ptr(op.in[1]) : nullptr;
+        int8_t* out;
+        long long out_batch_stride;
+        if (op.out_kind == 0) { out = tensor_ptr(op.out); out_batch_stride = (long long)op.h_out * op.w_out * op.cout_p; }
+        else if (op.out_kind == 1) { out = dev_out_cls; out_batch_stride = Np * m->hdr.n_classes; }
+        else { out = dev_out_box; out_batch_stride = Np * 4; }
+        bool taken = false;
+        if (int rc = launch_pw_umma(m, op, in, res, out, out_batch_stride, B, st, &taken)) return rc;
+        if (!taken) {
+          PwArgs a;
+          a.in = in; a.res = res; a.out = out;
+          a.w = reinterpret_cast<const int8_t*>(data(op.w_off));
+          a.bias = reinterpret_cast<const int32_t*>(data(op.bias_off));
+          a.mult = reinterpret_cast<const float*>(data(op.scale_off));
+          a.lut = reinterpret_cast<const int8_t*>(data(op.lut_off));
+          a.HW = op.h_in * op.w_in; a.M = (long long)B * a.HW;
+          a.cin_p = op.cin_p; a.cout = op.cout; a.cout_p = op.cout_p;
+          a.zp_conv = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
+          a.has_res = res != nullptr; a.res_zp = op.zp_in[1];
+          a.add_mult0 = op.add_mult[0]; a.add_mult1 = op.add_mult[1]; a.add_shift = op.add_shift;
+          a.zp_final = op.zp_in[2];
+          a.out_pix_stride = op.out_pix_stride; a.out_batch_stride = out_batch_stride;
+          a.out_elem_offset = op.out_elem_offset;
+          a.vector_out = (op.out_kind == 0);
+          dim3 grid((unsigned)((a.M + PW_BM - 1) / PW_BM), (unsigned)((op.cout_p + PW_BN - 1) / PW_BN));
+          pw_dp4a_kernel<<<grid, 256, 0, st>>>(a);
+        }
+        break;
+      }
+      default:
+        VBT_REQUIRE(false, "vbt_detect: unknown op type %d", op.type);
+    }
+    ++launched;
+    VBT_CHECK_CUDA(cudaPeekAtLastError());
+  }
+  vbt::count_launches(launched);
+  return VBT_OK;
+}

@@ -18,7 +18,7 @@
 
 namespace {
 
-constexpr int kMaxT = 64;   // live tracks per video
+constexpr int kMaxT = 256;  // live tracks per video (compile-time ceiling)
 constexpr int kMaxD = 32;   // detections per frame
 constexpr int NX = 7, NZ = 4;
 
@@ -274,6 +274,7 @@ __device__ int assign_min_cost(const double* cost, int ld, int n, int m, int* pa
         if (cur < minv[j]) { minv[j] = cur; way[j] = j0; }
         if (minv[j] < delta) { delta = minv[j]; j1 = j; }
       }
+      if (j1 == 0) return -1;          // NaN / inf costs: no augmenting column exists
       for (int j = 0; j <= M; ++j) {
         if (used[j]) { u[p[j]] += delta; v[j] -= delta; }
         else minv[j] -= delta;
@@ -301,25 +302,47 @@ __device__ int assign_min_cost(const double* cost, int ld, int n, int m, int* pa
   return cnt;
 }
 
-struct Shared {
-  double dets[kMaxD][6];
-  double tbox[kMaxT][4];        // predicted boxes, list order
-  double iou[kMaxD][kMaxT];
-  double cost[kMaxD][kMaxT];
-  int pair_d[kMaxD], pair_t[kMaxD];
-  int un_d[kMaxD * 2], un_t[kMaxT * 2];
+struct Shared {                 // carved from dynamic shared memory, ld = max_tracks
+  double (*dets)[6];            // [kMaxD][6]
+  double (*tbox)[4];            // [ld][4] predicted boxes, list order
+  double* iou;                  // [kMaxD][ld]
+  double* cost;                 // [kMaxD][ld]
+  int *pair_d, *pair_t;         // [kMaxD]
+  int *un_d, *un_t;             // [kMaxD], [ld]
+  unsigned char* nanflag;       // [ld]
+  int ld;
   int n_pairs, n_un_d, n_un_t, nd, nt, go;
-  unsigned char nanflag[kMaxT];
 };
+
+__host__ __device__ inline size_t shared_bytes(int ld) {
+  return sizeof(double) * (kMaxD * 6 + (size_t)ld * 4 + 2 * (size_t)kMaxD * ld) +
+         sizeof(int) * (3 * kMaxD + (size_t)ld) + (size_t)ld + 16;
+}
 
 __global__ void __launch_bounds__(32) tracker_update_kernel(
     Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
-    const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det,
+    const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det, int max_tracks,
     double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ Shared sh;
   const int v = blockIdx.x, lane = threadIdx.x;
+  if (lane == 0) {
+    unsigned char* p = dyn_smem;
+    sh.ld = max_tracks;
+    sh.dets = reinterpret_cast<double(*)[6]>(p); p += sizeof(double) * kMaxD * 6;
+    sh.tbox = reinterpret_cast<double(*)[4]>(p); p += sizeof(double) * 4 * (size_t)max_tracks;
+    sh.iou = reinterpret_cast<double*>(p); p += sizeof(double) * (size_t)kMaxD * max_tracks;
+    sh.cost = reinterpret_cast<double*>(p); p += sizeof(double) * (size_t)kMaxD * max_tracks;
+    sh.pair_d = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
+    sh.pair_t = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
+    sh.un_d = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
+    sh.un_t = reinterpret_cast<int*>(p); p += sizeof(int) * (size_t)max_tracks;
+    sh.nanflag = p;
+  }
+  __syncwarp();
+  const int ld = max_tracks;
   Video& vid = videos[v];
-  Trk* trk = tracks + (size_t)v * kMaxT;
+  Trk* trk = tracks + (size_t)v * max_tracks;
   const int nf = min(n_frames[v], F);
   const double vfps = fps[v];
   double* vrows = rows + (size_t)v * row_cap * VBT_ROW_COLS;
@@ -366,7 +389,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     // ---- first association round ----------------------------------------------------
     for (int i = lane; i < nd * nt; i += 32) {
       int d = i / nt, t = i % nt;
-      sh.iou[d][t] = iou_of(sh.dets[d], sh.tbox[t]);
+      sh.iou[d * ld + t] = iou_of(sh.dets[d], sh.tbox[t]);
     }
     __syncwarp();
     if (lane == 0) {
@@ -376,18 +399,18 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         int rmax = 0, cmax = 0;
         for (int d = 0; d < nd; ++d) {
           int c = 0;
-          for (int t = 0; t < nt; ++t) c += sh.iou[d][t] > prm.iou_threshold;
+          for (int t = 0; t < nt; ++t) c += sh.iou[d * ld + t] > prm.iou_threshold;
           rmax = max(rmax, c);
         }
         for (int t = 0; t < nt; ++t) {
           int c = 0;
-          for (int d = 0; d < nd; ++d) c += sh.iou[d][t] > prm.iou_threshold;
+          for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > prm.iou_threshold;
           cmax = max(cmax, c);
         }
         if (rmax == 1 && cmax == 1) {
           for (int d = 0; d < nd; ++d)
             for (int t = 0; t < nt; ++t)
-              if (sh.iou[d][t] > prm.iou_threshold) {
+              if (sh.iou[d * ld + t] > prm.iou_threshold) {
                 sh.pair_d[sh.n_pairs] = d; sh.pair_t[sh.n_pairs] = t; ++sh.n_pairs;
               }
         } else {
@@ -416,11 +439,13 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         double valid = (pb[4] >= 0) ? 1.0 : 0.0;
         double mult = prm.vdc_cls ? sh.dets[d][5] : sh.dets[d][4];
         double angle_cost = ((valid * ang) * prm.inertia) * mult;
-        sh.cost[d][t] = -(sh.iou[d][t] + angle_cost);
+        sh.cost[d * ld + t] = -(sh.iou[d * ld + t] + angle_cost);
       }
       __syncwarp();
-      if (lane == 0)
-        sh.n_pairs = assign_min_cost(&sh.cost[0][0], kMaxT, nd, nt, sh.pair_d, sh.pair_t);
+      if (lane == 0) {
+        sh.n_pairs = assign_min_cost(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t);
+        if (sh.n_pairs < 0) { sh.n_pairs = 0; vid.status = VBT_EINVAL; }
+      }
       __syncwarp();
     }
     if (lane == 0) {       // unmatched lists + low-IoU rejection, upstream order
@@ -433,7 +458,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       for (int t = 0; t < nt; ++t) if (!mt[t]) sh.un_t[nut++] = t;
       for (int i = 0; i < sh.n_pairs; ++i) {
         int d = sh.pair_d[i], t = sh.pair_t[i];
-        if (sh.iou[d][t] < prm.iou_threshold) { sh.un_d[nud++] = d; sh.un_t[nut++] = t; }
+        if (sh.iou[d * ld + t] < prm.iou_threshold) { sh.un_d[nud++] = d; sh.un_t[nut++] = t; }
         else { sh.pair_d[k] = d; sh.pair_t[k] = t; ++k; }
       }
       sh.n_pairs = k; sh.n_un_d = nud; sh.n_un_t = nut;
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       for (int i = lane; i < a_n * b_n; i += 32) {
         int a = i / b_n, b = i % b_n;
         const Trk& tk = trk[vid.order[sh.un_t[b]]];
-        sh.cost[a][b] = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
+        sh.cost[a * ld + b] = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
       }
       __syncwarp();
       if (lane == 0) {
@@ -456,21 +481,22 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         bool any_nan = false;
         for (int a = 0; a < a_n; ++a)
           for (int b = 0; b < b_n; ++b) {
-            double q = sh.cost[a][b];
+            double q = sh.cost[a * ld + b];
             if (isnan(q)) any_nan = true; else mx = fmax(mx, q);
           }
         sh.n_pairs = 0;
         if (!any_nan && mx > prm.iou_threshold) {
           for (int a = 0; a < a_n; ++a)
-            for (int b = 0; b < b_n; ++b) sh.iou[a][b] = -sh.cost[a][b];
+            for (int b = 0; b < b_n; ++b) sh.iou[a * ld + b] = -sh.cost[a * ld + b];
           int pr[kMaxD], pc[kMaxD];
-          int np = assign_min_cost(&sh.iou[0][0], kMaxT, a_n, b_n, pr, pc);
-          bool rm_d[kMaxD * 2], rm_t[kMaxT * 2];
+          int np = assign_min_cost(sh.iou, ld, a_n, b_n, pr, pc);
+          if (np < 0) { np = 0; vid.status = VBT_EINVAL; }
+          bool rm_d[kMaxD], rm_t[kMaxT];
           for (int a = 0; a < a_n; ++a) rm_d[a] = false;
           for (int b = 0; b < b_n; ++b) rm_t[b] = false;
           int k = 0;
           for (int i = 0; i < np; ++i) {
-            if (sh.cost[pr[i]][pc[i]] < prm.iou_threshold) continue;
+            if (sh.cost[pr[i] * ld + pc[i]] < prm.iou_threshold) continue;
             sh.pair_d[k] = sh.un_d[pr[i]]; sh.pair_t[k] = sh.un_t[pc[i]]; ++k;
             rm_d[pr[i]] = true; rm_t[pc[i]] = true;
           }
@@ -499,8 +525,8 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     if (lane == 0) {
       for (int i = 0; i < sh.n_un_d; ++i) {
         int slot = -1;
-        for (int s = 0; s < kMaxT; ++s) if (!vid.used[s]) { slot = s; break; }
-        if (slot < 0 || vid.n_tracks >= kMaxT) { vid.status = VBT_ECAPACITY; break; }
+        for (int s = 0; s < max_tracks; ++s) if (!vid.used[s]) { slot = s; break; }
+        if (slot < 0 || vid.n_tracks >= max_tracks) { vid.status = VBT_ECAPACITY; break; }
         vid.used[slot] = 1;
         trk_init(trk[slot], sh.dets[sh.un_d[i]], vid.next_id++);
         vid.order[vid.n_tracks++] = slot;
@@ -563,12 +589,12 @@ __global__ void tracker_reset_kernel(Video* videos, int V) {
   for (int i = 0; i < kMaxT; ++i) { vid.order[i] = 0; vid.used[i] = 0; }
 }
 
-__global__ void tracker_peek_kernel(const Video* videos, const Trk* tracks, int v, double* out,
-                                    int32_t* out_n) {
+__global__ void tracker_peek_kernel(const Video* videos, const Trk* tracks, int v, int max_tracks,
+                                    double* out, int32_t* out_n) {
   if (blockIdx.x || threadIdx.x) return;
   const Video& vid = videos[v];
   for (int t = 0; t < vid.n_tracks; ++t) {
-    const Trk& tk = tracks[(size_t)v * kMaxT + vid.order[t]];
+    const Trk& tk = tracks[(size_t)v * max_tracks + vid.order[t]];
     for (int j = 0; j < NX; ++j) out[t * 9 + j] = tk.x[j];
     out[t * 9 + 7] = (double)tk.id;
     out[t * 9 + 8] = (double)tk.tsu;
@@ -606,7 +632,10 @@ int vbt_tracker_create(int V, int max_tracks, const vbt_tracker_params* p, vbt_t
   t->prm.inertia = p->inertia; t->prm.max_age = p->max_age; t->prm.min_hits = p->min_hits;
   t->prm.delta_t = p->delta_t; t->prm.vdc_cls = p->vdc_uses_class_column;
   VBT_CHECK_CUDA(cudaMalloc(&t->videos, sizeof(Video) * (size_t)V));
-  VBT_CHECK_CUDA(cudaMalloc(&t->tracks, sizeof(Trk) * (size_t)V * kMaxT));
+  VBT_CHECK_CUDA(cudaMalloc(&t->tracks, sizeof(Trk) * (size_t)V * max_tracks));
+  VBT_CHECK_CUDA(cudaFuncSetAttribute(tracker_update_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)shared_bytes(kMaxT)));
   VBT_CHECK_CUDA(cudaMalloc(&t->peek, sizeof(double) * (kMaxT * 9)));
   VBT_CHECK_CUDA(cudaMalloc(&t->scratch, sizeof(int32_t) * (size_t)(V + 1)));
   *out = t;
@@ -635,9 +664,9 @@ int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* de
                   dev_rows && dev_row_count, "vbt_tracker_update: null pointer");
   VBT_REQUIRE(F > 0 && max_det > 0 && max_det <= kMaxD && row_cap > 0,
               "vbt_tracker_update: F=%d max_det=%d (<=%d) row_cap=%d", F, max_det, kMaxD, row_cap);
-  tracker_update_kernel<<<t->V, 32, 0, (cudaStream_t)stream>>>(
+  tracker_update_kernel<<<t->V, 32, shared_bytes(t->max_tracks), (cudaStream_t)stream>>>(
       t->videos, t->tracks, t->prm, dev_dets, dev_det_count, dev_frame_no, dev_fps, dev_n_frames,
-      F, max_det, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count);
+      F, max_det, t->max_tracks, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count);
   VBT_LAUNCHED(1);
   return VBT_OK;
 }
@@ -652,8 +681,12 @@ int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream) {
   VBT_CHECK_CUDA(cudaStreamSynchronize(st));
   for (int v = 0; v < t->V; ++v)
     if (host_status[v] != 0) {
+      if (host_status[v] == VBT_EINVAL) {
+        vbt::set_error("tracker video %d: association cost matrix held NaN/inf (degenerate boxes)", v);
+        return VBT_EINVAL;
+      }
       vbt::set_error("tracker video %d overflowed (more than %d live tracks, %d detections per "
-                     "frame, or the row table)", v, kMaxT, kMaxD);
+                     "frame, or the row table)", v, t->max_tracks, kMaxD);
       return VBT_ECAPACITY;
     }
   return VBT_OK;
@@ -662,7 +695,8 @@ int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream) {
 int vbt_tracker_peek(vbt_tracker* t, int v, double* host_tracks, void* stream) {
   VBT_REQUIRE(t && host_tracks && v >= 0 && v < t->V, "vbt_tracker_peek: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  tracker_peek_kernel<<<1, 1, 0, st>>>(t->videos, t->tracks, v, t->peek, t->scratch + t->V);
+  tracker_peek_kernel<<<1, 1, 0, st>>>(t->videos, t->tracks, v, t->max_tracks, t->peek,
+                                       t->scratch + t->V);
   VBT_LAUNCHED(1);
   int32_t n = 0;
   VBT_CHECK_CUDA(cudaMemcpyAsync(&n, t->scratch + t->V, sizeof(int32_t), cudaMemcpyDeviceToHost, st));

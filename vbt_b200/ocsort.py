@@ -18,7 +18,7 @@ import numpy as np
 
 from . import _lib
 
-MAX_TRACKS = 64
+MAX_TRACKS = 256
 MAX_DETS = 32
 
 

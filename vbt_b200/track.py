@@ -1,0 +1,122 @@
+"""`track.py`-compatible CLI and per-video driver on the B200 path.
+
+Same command line as the reference (track.py:65-72, including the misspelt
+``--detection_treshold``; ``--threads`` is accepted and ignored), same return value of
+``track()`` (track.py:129-260: dict of lists with keys id,time,x,y,dx,dy,
+norm_plate_height,norm_plate_width) and the same pickled DataFrame (track.py:103-126).
+
+Differences, all explicit:
+* ``--frame_stride`` (default 16 = HEAD's ``if frame_count % 16: continue``, track.py:166;
+  1 reproduces the bundled dfs_ocsort fixtures) and ``--batch`` (frames per GPU batch);
+* frames are decoded on the host by cv2 exactly as in the reference, then moved to the
+  GPU in batches; detection, tracking and row assembly run in CUDA;
+* the live preview (cv2.imshow, track.py:237-239) and the annotated video export
+  (track.py:152-154,241-242) are not built yet (SURVEY.md 8f "next"); asking for
+  ``--video_dir`` fails loudly instead of silently writing nothing.
+"""
+from __future__ import annotations
+
+import os
+
+import click
+import numpy as np
+
+from . import _lib
+from .interpreter import Interpreter
+from .pipeline import VideoPipeline, export_dataframe, rows_to_data
+
+MAX_AGE = 30     # track.py:22
+
+
+def track(src, interpreter, detection_treshold, display_image_height=720, video_path=None,
+          frame_stride=16, batch=64, return_pipeline_result=False):
+    """Runs detection + tracking over one video file and returns the captured data."""
+    import cv2
+    torch = _lib.require_cuda()
+    if video_path is not None:
+        raise NotImplementedError('annotated video export is not built yet (SURVEY.md 8f)')
+    cap = cv2.VideoCapture(src)
+    fps = cap.get(cv2.CAP_PROP_FPS)
+    det = interpreter.detector if isinstance(interpreter, Interpreter) else interpreter
+    if det.max_batch < batch:
+        det = type(det)(interpreter.model_path, max_batch=batch)
+    pipe = VideoPipeline(det, fps, detection_treshold,
+                         tracker_kw=dict(max_age=MAX_AGE, iou_threshold=0.1))   # track.py:157
+    staged, numbers = [], []
+    pinned = None
+    frame_count = 0
+
+    def flush():
+        nonlocal pinned
+        if not staged:
+            return
+        n = len(staged)
+        h, w = staged[0].shape[:2]
+        if pinned is None or pinned.shape[1:3] != (h, w):
+            pinned = torch.empty((batch, h, w, 3), dtype=torch.uint8).pin_memory()
+        for i, f in enumerate(staged):
+            pinned[i].copy_(torch.from_numpy(f))
+        dev = pinned[:n].to('cuda', non_blocking=True)
+        nums = torch.as_tensor(np.asarray(numbers, dtype=np.int32), device='cuda')
+        pipe.process(dev, nums, swap_rb=True)          # cv2 frames are BGR (track.py:171)
+        staged.clear()
+        numbers.clear()
+
+    while cap.isOpened():
+        ret, frame = cap.read()
+        frame_count += 1                               # counts from 1, before the ret check
+        if not ret:
+            break
+        if frame_count % frame_stride:
+            continue
+        staged.append(frame)
+        numbers.append(frame_count)
+        if len(staged) == batch:
+            flush()
+    flush()
+    cap.release()
+    result = pipe.finish()
+    data = rows_to_data(result['rows'])
+    return (data, result) if return_pipeline_result else data
+
+
+@click.command()
+@click.argument('src', type=str, nargs=-1)
+@click.option('--model', default='models/efficientdet_lite0_whole.tflite', type=str, show_default=True,
+              help='Model: a .tflite / .vbtm file or synthetic:lite0|lite1|lite2.')
+@click.option('--detection_treshold', default=0.5, type=float, show_default=True,
+              help='Object detection threshold.')
+@click.option('--display_image_height', default=720, type=int, show_default=True,
+              help='Displayed image height in pixels (preview is not built; accepted for compatibility).')
+@click.option('--df_dir', default=None, show_default=True,
+              help="Directory for exporting the dataframes. If not set the dataframe won't be exported.")
+@click.option('--video_dir', default=None, show_default=True,
+              help='Directory for exporting the annotated video (not built yet).')
+@click.option('--threads', default=4, show_default=True,
+              help='Accepted for compatibility; inference runs on the GPU.')
+@click.option('--frame_stride', default=16, show_default=True,
+              help='Process every n-th frame (reference HEAD: 16; fixtures: 1).')
+@click.option('--batch', default=64, show_default=True, help='Frames per GPU batch.')
+def main(src, model, detection_treshold, display_image_height, df_dir, video_dir, threads,
+         frame_stride, batch):
+    """Track weight plates in the given videos and export the per-frame dataframes."""
+    if df_dir is not None:
+        os.makedirs(df_dir, exist_ok=True)
+    if video_dir is not None:
+        os.makedirs(video_dir, exist_ok=True)
+    for s in src:
+        if not os.path.isfile(s):
+            raise FileNotFoundError()
+        interpreter = Interpreter(model_path=model, num_threads=threads)
+        interpreter.allocate_tensors()
+        video_path = None
+        if video_dir is not None:
+            video_path = os.path.join(video_dir, f'{os.path.basename(s).split(".")[0]}.mp4')
+        data = track(s, interpreter, detection_treshold, display_image_height, video_path,
+                     frame_stride=frame_stride, batch=batch)
+        if df_dir is not None:
+            export_dataframe(data, s, model, df_dir)
+
+
+if __name__ == '__main__':
+    main()
