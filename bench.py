@@ -1,0 +1,409 @@
+#!/usr/bin/env python
+"""Throughput bench for the vbt hot path on B200 (contract: see the task prompt / DESIGN.md).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port), rank 0
+
+A *step* is one pass of the whole hot path (K1 preprocess -> EfficientDet-Lite0 int8 ->
+K6 post-process -> threshold/pack -> K7 tracker -> K8 velocity) over one batch of 64
+synthetic 1080p frames of a 1800-frame, 30 fps clip (BASELINE.json configs[1], frame
+stride 1).  `value` = frames/s with the clip already resident in HBM; `e2e` = the same
+with frames starting in pinned HOST memory (H2D inside the timed region, per-step result
+read back).  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'frames/sec (detect+track+velocity, 1080p, Lite0)'
+H, W = 1080, 1920
+CLIP_FRAMES, FPS, BATCH = 1800, 30.0, 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=58)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--variant', default='lite0')
+    ap.add_argument('--batch', type=int, default=BATCH)
+    ap.add_argument('--clip-frames', type=int, default=CLIP_FRAMES)
+    ap.add_argument('--cpu-sample', type=int, default=12, help='frames timed for cpu_baseline')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), float(p['bf16_tflops_sustained']), 'measured'
+    except Exception:
+        return 6650.0, 1400.0, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); smax.append(float(p[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, p[5:9]):
+                if v.lower().startswith('active'):
+                    reasons.add(n)
+        return {'sm_mhz': float(np.median(sm)) if sm else None,
+                'sm_max_mhz': max(smax) if smax else None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def op_algorithmic(g, op, E):
+    """(kernel name, algorithmic bytes, flops) of one layer-program op for ONE frame:
+    logical input + output activation elements + weights, 1 byte each."""
+    ins = [g.tensors[i] for i in op.inputs]
+    if op.out >= 0:
+        t = g.tensors[op.out]
+        out_el = t.h * t.w * t.c
+    else:
+        out_el = ins[0].h * ins[0].w * g.out_channels(op)
+    in_el = sum(t.h * t.w * t.c for t in ins)
+    if op.type == E.OP_PW:
+        cout = g.out_channels(op)
+        w = ins[0].c * cout + 8 * cout
+        if op.residual >= 0:
+            r = g.tensors[op.residual]
+            in_el += r.h * r.w * r.c
+        return 'pw', in_el + out_el + w, 2 * ins[0].h * ins[0].w * ins[0].c * cout
+    if op.type == E.OP_DW:
+        t = g.tensors[op.out]
+        return f'dw{op.k}', in_el + out_el + t.c * (op.k * op.k + 8), 2 * t.h * t.w * t.c * op.k * op.k
+    if op.type == E.OP_STEM:
+        t = g.tensors[op.out]
+        return 'stem', in_el + out_el + t.c * 35, 2 * t.h * t.w * t.c * 27
+    if op.type == E.OP_ADD:
+        return 'fuse_add', in_el + out_el, in_el
+    return 'maxpool', in_el + out_el, in_el
+
+
+def run_reference(args, rank):
+    """CPU arm: the oracle port of the reference path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    import torch
+    from oracle.cpu_pipeline import CpuPipeline
+    from vbt_b200 import effdet
+    from vbt_b200.synth import plate_trajectory
+    g = effdet.build_synthetic(args.variant)
+    per_step = max(1, min(4, 60 // max(args.steps, 1)))
+    rng = np.random.default_rng(0)
+    bg = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    traj = plate_trajectory(args.clip_frames, FPS)
+    yy, xx = np.mgrid[0:H, 0:W]
+
+    def frame(i):
+        f = bg.copy()
+        x, y, w, h = traj[i % len(traj)]
+        f[((yy - y * H) / (h * H / 2)) ** 2 + ((xx - x * W) / (w * W / 2)) ** 2 <= 1.0] = 40
+        return f
+
+    frames = [frame(i) for i in range(per_step * 4)]
+    pipe = CpuPipeline(g, FPS, 0.5)
+    n = 0
+    for _ in range(args.warmup):
+        for _ in range(per_step):
+            pipe.step(frames[n % len(frames)], n + 1); n += 1
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        for _ in range(per_step):
+            pipe.step(frames[n % len(frames)], n + 1); n += 1
+    pipe.finish()
+    dt = time.perf_counter() - t0
+    v = args.steps * per_step / dt
+    cores = torch.get_num_threads()
+    sample = (f'{args.steps} steps x {per_step} frame(s) of the same synthetic 1080p clip, batch 1 per '
+              f'frame like track.py; int8-exact oracle (fp64 conv on torch CPU), all host threads')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8',
+        'data': 'synthetic',
+        'config': {'workload': 'EfficientDet-Lite0 full track.py pipeline, synthetic 1080p clip, '
+                               'CPU port of the reference path (TFLite runtime and weights are '
+                               'absent from the reference checkout)', 'frames_per_step': per_step},
+        'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if args.impl == 'reference':
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from vbt_b200 import _lib, effdet
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    from vbt_b200.synth import plate_trajectory, render_clip
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    B = args.batch
+    g = effdet.build_synthetic(args.variant)
+    det = Detector(g, max_batch=B)
+    pipe = VideoPipeline(det, FPS, 0.5, row_cap=1 << 17)
+    # every rank owns one whole video (weak scaling: videos are the shard unit)
+    clip = render_clip(args.clip_frames, H, W, seed=rank, device='cuda',
+                       trajectory=plate_trajectory(args.clip_frames, FPS, seed=rank))
+    n_batches = (args.clip_frames + B - 1) // B
+    numbers = torch.arange(1, args.clip_frames + 1, dtype=torch.int32, device='cuda')
+    state = {'cursor': 0, 'frames': 0, 'videos': 0}
+
+    def batch_range(b):
+        return b * B, min((b + 1) * B, args.clip_frames)
+
+    def one_step(src=None):
+        b = state['cursor'] % n_batches
+        if b == 0 and state['cursor'] > 0:
+            state['last'] = pipe.finish()          # end of the clip: phases + rows to the host
+            pipe.reset()
+            state['videos'] += 1
+        s, e = batch_range(b)
+        pipe.process(clip[s:e] if src is None else src[:e - s], numbers[s:e], swap_rb=True)
+        state['cursor'] += 1
+        state['frames'] += e - s
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_tables():
+        """The one exchange step: counts, then padded row tables, over NCCL."""
+        if world == 1:
+            return
+        cnt = pipe.tracker.row_count.clone()
+        counts = [torch.zeros_like(cnt) for _ in range(world)]
+        dist.all_gather(counts, cnt)
+        mx = int(max(int(c.item()) for c in counts))
+        pad = pipe.tracker.rows[0, :max(mx, 1)].contiguous()
+        out = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(out, pad)
+
+    # ---- device-resident throughput (`value`) -------------------------------------------
+    for _ in range(args.warmup):
+        one_step()
+    det.profile(True)
+    pipe.stage_events = []
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = _lib.lib().vbt_launch_count()
+    frames0 = state['frames']
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        one_step()
+    gather_tables()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    frames = state['frames'] - frames0
+    launches = _lib.lib().vbt_launch_count() - launches0
+    op_ms, calls = det.op_times()
+    det.profile(False)
+    stage_events, pipe.stage_events = pipe.stage_events, None
+    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    ft = torch.tensor([float(frames)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ft, op=dist.ReduceOp.SUM)
+    ms_max, frames_all = float(t.item()), float(ft.item())
+    value = frames_all / (ms_max / 1e3)
+
+    # ---- per-kernel breakdown + roofline of the dominant kernel ---------------------------
+    stage_names = ['K1_preprocess', 'network', 'K6_postprocess', 'pack', 'K7_tracker', 'K8_velocity']
+    stage_ms = dict.fromkeys(stage_names, 0.0)
+    for marks in stage_events:
+        for nme, a, b_ in zip(stage_names, marks[:-1], marks[1:]):
+            stage_ms[nme] += a.elapsed_time(b_)
+    kern = {}
+    frames_prof = frames * (calls / max(args.steps, 1)) if calls else frames
+    for op, tms in zip(g.ops, op_ms):
+        name, by, fl = op_algorithmic(g, op, effdet)
+        k = kern.setdefault(name, {'ms': 0.0, 'bytes_per_frame': 0, 'flops_per_frame': 0, 'launches_per_step': 0})
+        k['ms'] += float(tms); k['bytes_per_frame'] += by; k['flops_per_frame'] += fl
+        k['launches_per_step'] += 1
+    k1_bytes = H * W * 3 + g.S * g.S * 3
+    kern['K1_preprocess'] = {'ms': stage_ms['K1_preprocess'], 'bytes_per_frame': k1_bytes,
+                             'flops_per_frame': 0, 'launches_per_step': 1}
+    for nme in ('K6_postprocess', 'pack', 'K7_tracker', 'K8_velocity'):
+        kern[nme] = {'ms': stage_ms[nme], 'bytes_per_frame': 0, 'flops_per_frame': 0, 'launches_per_step': 1}
+    total_kernel_ms = sum(k['ms'] for k in kern.values()) or 1.0
+    hbm_peak, tf_peak, peak_src = measured_peaks()
+    dom_name = max(kern, key=lambda n: kern[n]['ms'])
+    dom = kern[dom_name]
+    dom_gbs = dom['bytes_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e9 if dom['ms'] > 0 else 0.0
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+            traffic = json.load(f).get(dom_name)
+    except Exception:
+        pass
+    roofline = {'kernel': dom_name, 'bound': 'hbm', 'achieved': dom_gbs, 'peak': hbm_peak,
+                'unit': 'GB/s', 'frac': dom_gbs / hbm_peak, 'traffic': traffic,
+                'peak_source': f'{peak_src} (MEASURED_PEAKS.json hbm_gbs)',
+                'share_of_step': dom['ms'] / total_kernel_ms,
+                'algorithmic_bytes_per_frame': dom['bytes_per_frame'],
+                'avg_launch_us': 1e3 * dom['ms'] / max(dom['launches_per_step'] * max(calls, 1), 1),
+                'tensor_tflops': dom['flops_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e12 if dom['ms'] > 0 else 0.0}
+    breakdown = {n: {'share': k['ms'] / total_kernel_ms,
+                     'gbs': (k['bytes_per_frame'] * frames_prof / (k['ms'] / 1e3) / 1e9) if k['ms'] > 0 and k['bytes_per_frame'] else None,
+                     'ms_per_step': k['ms'] / max(args.steps, 1)}
+                 for n, k in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])}
+
+    # ---- end to end from pinned host memory ------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        ring = 3
+        host = [torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(ring)]
+        for i in range(ring):
+            s, e = batch_range(i % n_batches)
+            host[i][:e - s].copy_(clip[s:e])
+        stage = [torch.empty((B, H, W, 3), dtype=torch.uint8, device='cuda') for _ in range(2)]
+        res_host = torch.empty((B, det.max_det * 6 + 2), dtype=torch.float32).pin_memory()
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
+        main_stream = torch.cuda.current_stream()
+        h2d_bytes = B * H * W * 3
+        d2h_bytes = res_host.numel() * 4
+
+        def e2e_step(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[slot])
+                stage[slot].copy_(host[i % ring], non_blocking=True)
+                ready[slot].record(copy_stream)
+            main_stream.wait_event(ready[slot])
+            one_step(stage[slot])
+            n = B
+            res = torch.cat([det.boxes[:n].reshape(n, -1), det.scores[:n],
+                             det.count[:n, None], pipe.tracker.row_count.float().expand(n, 1)], dim=1)
+            res_host.copy_(res, non_blocking=True)
+            freed[slot].record(main_stream)
+
+        for s_ in range(2):
+            freed[s_].record(main_stream)
+        for i in range(args.warmup):
+            e2e_step(i)
+        barrier()
+        f0 = state['frames']
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        gather_tables()
+        b_.record()
+        barrier()
+        ems = torch.tensor([a.elapsed_time(b_)], dtype=torch.float64, device='cuda')
+        efr = torch.tensor([float(state['frames'] - f0)], dtype=torch.float64, device='cuda')
+        if world > 1:
+            dist.all_reduce(ems, op=dist.ReduceOp.MAX)
+            dist.all_reduce(efr, op=dist.ReduceOp.SUM)
+        e2e = {'value': float(efr.item()) / (float(ems.item()) / 1e3), 'unit': 'frames/s',
+               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
+               'ms_per_step': float(ems.item()) / args.steps}
+
+    # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.cpu_pipeline import CpuPipeline
+        n = args.cpu_sample
+        sample = clip[:n].cpu().numpy()
+        cp = CpuPipeline(g, FPS, 0.5)
+        cp.step(sample[0], 1)
+        cp.reset()
+        t0 = time.perf_counter()
+        for i in range(n):
+            cp.step(sample[i], i + 1)
+        cp.finish()
+        dt = time.perf_counter() - t0
+        cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+               'sample': f'first {n} frames of the same clip, one frame per invoke like track.py; '
+                         f'int8-exact oracle chain (numpy + torch-CPU fp64 conv), not TFLite/XNNPACK'}
+
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
+            'config': {
+                'workload': 'configs[1]: EfficientDet-Lite0 (synthetic int8 weights) full track.py '
+                            'pipeline on one synthetic 1080p 30 fps 60 s clip per GPU, frame batch 64, '
+                            'frame stride 1',
+                'variant': args.variant, 'batch': B, 'clip_frames': args.clip_frames,
+                'frames_per_timed_region': frames_all, 'videos_finished': state['videos'],
+                'cache': 'inputs larger than L2: 398 MB of frames per step vs 126 MB L2, no flush needed',
+                'parallelism': f'{world} video shard(s), one per GPU, NCCL gather of row tables at the end',
+            },
+            'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
+            'clocks': clocks, 'kernels': breakdown,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -58,14 +58,21 @@ typedef struct vbt_model vbt_model;
 int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out);
 void vbt_model_destroy(vbt_model* m);
 /* info[0]=input size S, [1]=anchors N, [2]=workspace bytes per frame, [3]=ops,
- * [4]=classes, [5]=kernels launched per vbt_detect call */
+ * [4]=classes, [5]=kernels launched per vbt_detect call, [6]=Np (N rounded up to 16) */
 int vbt_model_info(const vbt_model* m, long long info[8]);
-/* in: u8 [B,S,S,3] RGB; out_cls: i8 [B,N] post-LOGISTIC scores (scale 1/256, zp -128);
- * out_box: i8 [B,N,4] (ty,tx,th,tw) with the model's box quantisation.
+/* in: u8 [B,S,S,3] RGB; out_cls: i8 [B,Np] post-LOGISTIC scores (scale 1/256, zp -128);
+ * out_box: i8 [B,Np,4] (ty,tx,th,tw) with the model's box quantisation; Np = info[6] =
+ * N rounded up to 16 (row stride; the pad entries are never read).
  * workspace: >= B * info[2] bytes, 256-byte aligned. */
 int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace,
                size_t workspace_bytes, int8_t* dev_out_cls, int8_t* dev_out_box,
                void* stream);
+
+/* Per-op device timing for bench.py's roofline: while enabled, vbt_detect brackets every
+ * op with CUDA events on its stream; vbt_model_op_times synchronises and returns the
+ * accumulated milliseconds per op (host f64 [ops]) and the number of calls covered. */
+int vbt_model_profile(vbt_model* m, int enable);
+int vbt_model_op_times(vbt_model* m, double* host_ms, long long* calls);
 
 /* ---- K6 detection post-processing --------------------------------------------------
  * replaces: the TFLite_Detection_PostProcess custom op inside signature_fn (odt.py:61)

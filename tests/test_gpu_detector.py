@@ -127,8 +127,9 @@ def test_pack_detections_matches_odt_helpers():
     dets = torch.zeros((F, D, 6), dtype=torch.float64, device='cuda')
     n = torch.zeros(F, dtype=torch.int32, device='cuda')
     dev = lambda a: torch.as_tensor(np.ascontiguousarray(a), device='cuda')
-    _lib.check(_lib.lib().vbt_pack_detections(dev(boxes).data_ptr(), dev(scores).data_ptr(),
-                                              dev(count).data_ptr(), F, D, 0.5, dets.data_ptr(),
+    d_boxes, d_scores, d_count = dev(boxes), dev(scores), dev(count)     # keep alive
+    _lib.check(_lib.lib().vbt_pack_detections(d_boxes.data_ptr(), d_scores.data_ptr(),
+                                              d_count.data_ptr(), F, D, 0.5, dets.data_ptr(),
                                               n.data_ptr(), _lib.stream_ptr()))
     dets, n = dets.cpu().numpy(), n.cpu().numpy()
     for f in range(F):

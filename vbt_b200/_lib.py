@@ -46,6 +46,8 @@ PROTOTYPES = {
     'vbt_model_destroy': (None, [_P]),
     'vbt_model_info': (_I, [_P, C.POINTER(C.c_longlong)]),
     'vbt_detect': (_I, [_P, _P, _I, _P, _SZ, _P, _P, _P]),
+    'vbt_model_profile': (_I, [_P, _I]),
+    'vbt_model_op_times': (_I, [_P, _P, C.POINTER(C.c_longlong)]),
     'vbt_postprocess_q8': (_I, [_P, _P, _P, _I, _F, _I, _I, _P, _P, _P, _P, _P, _P]),
     'vbt_pack_detections': (_I, [_P, _P, _P, _I, _I, _F, _P, _P, _P]),
     'vbt_tracker_create': (_I, [_I, _I, C.POINTER(TrackerParams), C.POINTER(_P)]),

@@ -7,6 +7,33 @@
 
 using namespace vbt;
 
+static int harvest_one(vbt_model* m) {
+  const int n = (int)m->ops.size();
+  const int set = (m->prof_head - m->prof_pending + vbt_model::kProfRing * 2) % vbt_model::kProfRing;
+  cudaEvent_t* ev = m->prof_events.data() + (size_t)set * (n + 1);
+  VBT_CHECK_CUDA(cudaEventSynchronize(ev[n]));
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    VBT_CHECK_CUDA(cudaEventElapsedTime(&ms, ev[i], ev[i + 1]));
+    m->prof_ms[i] += ms;
+  }
+  m->prof_pending -= 1;
+  m->prof_calls += 1;
+  return VBT_OK;
+}
+
+namespace vbt {
+// called by vbt_detect: returns the event set to record into (nullptr = profiling off)
+cudaEvent_t* profile_begin(vbt_model* m) {
+  if (!m->profile) return nullptr;
+  if (m->prof_pending == vbt_model::kProfRing && harvest_one(m) != VBT_OK) return nullptr;
+  cudaEvent_t* ev = m->prof_events.data() + (size_t)m->prof_head * (m->ops.size() + 1);
+  m->prof_head = (m->prof_head + 1) % vbt_model::kProfRing;
+  m->prof_pending += 1;
+  return ev;
+}
+}  // namespace vbt
+
 extern "C" {
 
 int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
@@ -79,6 +106,7 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
 
 void vbt_model_destroy(vbt_model* m) {
   if (!m) return;
+  for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   if (m->dev_data) cudaFree(m->dev_data);
   delete m;
 }
@@ -93,6 +121,31 @@ int vbt_model_info(const vbt_model* m, long long info[8]) {
   info[5] = m->kernels_per_detect;
   info[6] = m->hdr.n_anchors_pad;
   info[7] = 0;
+  return VBT_OK;
+}
+
+int vbt_model_profile(vbt_model* m, int enable) {
+  VBT_REQUIRE(m, "vbt_model_profile: null handle");
+  if (enable && m->prof_events.empty()) {
+    const size_t n = (size_t)vbt_model::kProfRing * (m->ops.size() + 1);
+    m->prof_events.resize(n);
+    for (size_t i = 0; i < n; ++i) VBT_CHECK_CUDA(cudaEventCreate(&m->prof_events[i]));
+    m->prof_ms.assign(m->ops.size(), 0.0);
+  }
+  if (enable && !m->profile) {
+    m->prof_ms.assign(m->ops.size(), 0.0);
+    m->prof_calls = 0; m->prof_pending = 0; m->prof_head = 0;
+  }
+  m->profile = enable != 0;
+  return VBT_OK;
+}
+
+int vbt_model_op_times(vbt_model* m, double* host_ms, long long* calls) {
+  VBT_REQUIRE(m && host_ms && calls, "vbt_model_op_times: null pointer");
+  while (m->prof_pending > 0)
+    if (int rc = harvest_one(m)) return rc;
+  for (size_t i = 0; i < m->ops.size(); ++i) host_ms[i] = i < m->prof_ms.size() ? m->prof_ms[i] : 0.0;
+  *calls = m->prof_calls;
   return VBT_OK;
 }
 

@@ -90,4 +90,11 @@ struct vbt_model {
   const float* dev_exp_lut = nullptr;
   int kernels_per_detect = 0;
   int device = -1;
+  // optional per-op timing (bench.py): a ring of event sets, harvested lazily
+  bool profile = false;
+  static constexpr int kProfRing = 64;
+  std::vector<cudaEvent_t> prof_events;   // [kProfRing][n_ops + 1]
+  std::vector<double> prof_ms;            // [n_ops] accumulated
+  int prof_head = 0, prof_pending = 0;    // sets recorded and not yet harvested
+  long long prof_calls = 0;
 };

@@ -18,6 +18,7 @@
 #include "model.cuh"
 
 namespace vbt {
+cudaEvent_t* profile_begin(vbt_model* m);
 int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res,
                    int8_t* out, long long out_batch_stride, int B, cudaStream_t st, bool* taken);
 }
@@ -363,6 +364,8 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
   };
   auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
   int launched = 0;
+  cudaEvent_t* prof = profile_begin(m);
+  if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], st));
   for (const OpRecord& op : m->ops) {
     switch (op.type) {
       case OP_STEM: {
@@ -444,6 +447,7 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
     }
     ++launched;
     VBT_CHECK_CUDA(cudaPeekAtLastError());
+    if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], st));
   }
   vbt::count_launches(launched);
   return VBT_OK;

@@ -75,6 +75,17 @@ class Detector:
         if h:
             _lib.lib().vbt_model_destroy(h)
 
+    # -- per-op device timing (bench.py) -----------------------------------------------------
+    def profile(self, enable=True):
+        _lib.check(_lib.lib().vbt_model_profile(self.handle, int(enable)))
+
+    def op_times(self):
+        """(ms per op accumulated [n_ops], number of vbt_detect calls covered)."""
+        ms = np.zeros(max(self.n_ops, 1), dtype=np.float64)
+        calls = C.c_longlong(0)
+        _lib.check(_lib.lib().vbt_model_op_times(self.handle, _lib.ptr(ms), C.byref(calls)))
+        return ms[:self.n_ops], int(calls.value)
+
     # -- stages ----------------------------------------------------------------------------
     def preprocess(self, frames, swap_rb=True, stream=None):
         """frames: uint8 CUDA tensor [B,H,W,3] -> self.resized[:B] (RGB, SxS)."""

@@ -42,6 +42,13 @@ class VideoPipeline:
         self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda')
         self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
         self.frames_done = 0
+        self.stage_events = None      # bench.py: list of per-step event tuples when profiling
+
+    def _mark(self, marks):
+        if marks is not None:
+            e = self.torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append(e)
 
     def reset(self, fps=None):
         if fps is not None:
@@ -56,19 +63,32 @@ class VideoPipeline:
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
         tensor [n] with the 1-based frame_count of each (track.py:161)."""
         n = frames.shape[0]
-        boxes, _, scores, count, _ = self.det.detect(frames, swap_rb, self.threshold, stream)
+        marks = [] if self.stage_events is not None else None
+        self._mark(marks)
+        det = self.det
+        images = det.preprocess(frames, swap_rb, stream)
+        self._mark(marks)
+        det.network(images, stream)
+        self._mark(marks)
+        boxes, _, scores, count, _ = det.postprocess(n, score_to_q(self.threshold), stream=stream)
+        self._mark(marks)
         sp = _lib.stream_ptr(stream)
         _lib.check(_lib.lib().vbt_pack_detections(
             boxes.data_ptr(), scores.data_ptr(), count.data_ptr(), n, self.det.max_det,
             self.threshold, self.dets.data_ptr(), self.det_count.data_ptr(), sp))
         self.frame_no[0, :n].copy_(frame_numbers, non_blocking=True)
         self.n_frames.fill_(n)
+        self._mark(marks)
         self.tracker.update(self.dets, self.det_count, self.frame_no, self.d_fps, self.n_frames,
                             stream=stream)
+        self._mark(marks)
         self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
                           self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
                           self.plate_diameter, self.diff_threshold, self.min_distance,
                           smooth=True, finish=False)
+        self._mark(marks)
+        if marks is not None:
+            self.stage_events.append(marks)
         self.frames_done += n
 
     def finish(self):

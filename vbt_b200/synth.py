@@ -41,7 +41,8 @@ def plate_trajectory(n_frames, fps=30.0, reps=6, seed=0):
 
 def render_clip(n_frames, height=1080, width=1920, seed=0, device='cuda', chunk=32,
                 trajectory=None):
-    """uint8 [n_frames,height,width,3] BGR clip on `device` (torch), seed-deterministic."""
+    """uint8 [n_frames,height,width,3] BGR clip on `device` (torch), seed-deterministic:
+    a static uniform-noise scene (fixed camera) with one dark plate moving over it."""
     import torch
     g = torch.Generator(device=device)
     g.manual_seed(seed)
@@ -49,10 +50,10 @@ def render_clip(n_frames, height=1080, width=1920, seed=0, device='cuda', chunk=
     out = torch.empty((n_frames, height, width, 3), dtype=torch.uint8, device=device)
     yy = torch.arange(height, device=device, dtype=torch.float32)[:, None]
     xx = torch.arange(width, device=device, dtype=torch.float32)[None, :]
+    bg = torch.randint(0, 256, (height, width, 3), dtype=torch.uint8, device=device, generator=g)
     for s in range(0, n_frames, chunk):
         e = min(s + chunk, n_frames)
-        out[s:e] = torch.randint(0, 256, (e - s, height, width, 3), dtype=torch.uint8,
-                                 device=device, generator=g)
+        out[s:e] = bg
         for i in range(s, e):
             x, y, w, h = (float(v) for v in traj[i])
             m = ((yy - y * height) / (h * height / 2)) ** 2 + \
