@@ -321,7 +321,7 @@ def main():
             s, e = batch_range(i % n_batches)
             host[i][:e - s].copy_(clip[s:e])
         stage = [torch.empty((B, H, W, 3), dtype=torch.uint8, device='cuda') for _ in range(2)]
-        res_host = torch.empty((B, det.max_det * 6 + 2), dtype=torch.float32).pin_memory()
+        res_host = torch.empty((B, det.max_det * 5 + 2), dtype=torch.float32).pin_memory()
         copy_stream = torch.cuda.Stream()
         ready = [torch.cuda.Event() for _ in range(2)]
         freed = [torch.cuda.Event() for _ in range(2)]

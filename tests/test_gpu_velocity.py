@@ -41,7 +41,7 @@ def test_figs_ocsort_labels_34_of_34():
 def test_velocity_tracker_class_streaming():
     """The drop-in class fed one sample at a time, results read mid-stream."""
     from vbt_b200.velocity import VelocityTracker, Phase
-    series = helpers.all_series()[:3]
+    series = [s for s in helpers.all_series() if len(s[2]) > 2][:3]
     for key, raw, want in series:
         sm = ov.smooth_rows(raw)
         vt = VelocityTracker(0.45)
@@ -53,8 +53,9 @@ def test_velocity_tracker_class_streaming():
                 assert np.array_equal(phases_array(vt.phases), mid)
         vt.end_processing()
         assert np.array_equal(phases_array(vt.phases), want), key
-        assert str(vt.phases[0]).startswith(('concentric', 'eccentric'))
-        assert vt.phases[0].duration == vt.phases[0].time_end - vt.phases[0].time_start
+        for ph in vt.phases[:1]:
+            assert str(ph).startswith(('concentric', 'eccentric'))
+            assert ph.duration == ph.time_end - ph.time_start and ph.y_diff == abs(ph.y_start - ph.y_end)
 
 
 def test_random_series_vs_oracle():

@@ -48,65 +48,89 @@ struct Params {
   int max_age, min_hits, delta_t, vdc_cls;
 };
 
-__device__ __forceinline__ void mm(const double* a, const double* b, double* c, int n, int m,
-                                   int p) {   // c[n,p] = a[n,m] * b[m,p], k ascending
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < p; ++j) {
-      double acc = 0.0;
-      for (int k = 0; k < m; ++k) acc = acc + a[i * m + k] * b[k * p + j];
-      c[i * p + j] = acc;
-    }
-}
-
-// c[n,p] = a[n,m] * b[p,m]^T
-__device__ __forceinline__ void mmt(const double* a, const double* b, double* c, int n, int m,
-                                    int p) {
-  for (int i = 0; i < n; ++i)
-    for (int j = 0; j < p; ++j) {
-      double acc = 0.0;
-      for (int k = 0; k < m; ++k) acc = acc + a[i * m + k] * b[j * m + k];
-      c[i * p + j] = acc;
-    }
-}
-
-__device__ void kf_predict(double* x, double* P) {
-  double F[NX * NX], t[NX * NX], nx[NX];
-  for (int i = 0; i < NX * NX; ++i) F[i] = 0.0;
-  for (int i = 0; i < NX; ++i) F[i * NX + i] = 1.0;
-  F[0 * NX + 4] = F[1 * NX + 5] = F[2 * NX + 6] = 1.0;
-  mm(F, x, nx, NX, NX, 1);
-  for (int i = 0; i < NX; ++i) x[i] = nx[i];
-  mm(F, P, t, NX, NX, NX);
-  mmt(t, F, P, NX, NX, NX);
+// The oracle multiplies dense 7x7 matrices k-ascending.  F = I + shift and H = [I4 0] are
+// 0/1 matrices, so every dense inner product below collapses to the few terms written
+// out here IN THE SAME ORDER; the skipped terms are exact zeros (0 * finite), which do
+// not change an IEEE sum.  Everything is unrolled over constant indices so x and P live
+// in registers.
+__device__ __forceinline__ void kf_predict(double* x, double* P) {
+  // x = F x
+  x[0] = x[0] + x[4]; x[1] = x[1] + x[5]; x[2] = x[2] + x[6];
+  // t = F P : rows 0..2 pick up rows 4..6
+  double t[NX * NX];
+#pragma unroll
+  for (int j = 0; j < NX; ++j) {
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+      t[i * NX + j] = (i < 3) ? P[i * NX + j] + P[(i + 4) * NX + j] : P[i * NX + j];
+  }
+  // P = t F^T + Q : columns 0..2 pick up columns 4..6
   const double q[NX] = {1.0, 1.0, 1.0, 1.0, 0.01, 0.01, 0.0001};
-  for (int i = 0; i < NX; ++i) P[i * NX + i] = P[i * NX + i] + q[i];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      double v = (j < 3) ? t[i * NX + j] + t[i * NX + j + 4] : t[i * NX + j];
+      P[i * NX + j] = (i == j) ? v + q[i] : v;
+    }
+  }
 }
 
-__device__ void kf_correct(double* x, double* P, const double* z) {
-  double H[NZ * NX], R[NZ * NZ];
-  for (int i = 0; i < NZ * NX; ++i) H[i] = 0.0;
-  for (int i = 0; i < NZ; ++i) H[i * NX + i] = 1.0;
-  for (int i = 0; i < NZ * NZ; ++i) R[i] = 0.0;
-  R[0] = 1.0; R[5] = 1.0; R[10] = 10.0; R[15] = 10.0;
-  double hx[NZ], y[NZ], pht[NX * NZ], s[NZ * NZ], si[NZ * NZ], k[NX * NZ], ky[NX];
-  mm(H, x, hx, NZ, NX, 1);
-  for (int i = 0; i < NZ; ++i) y[i] = z[i] - hx[i];
-  mmt(P, H, pht, NX, NX, NZ);
-  mm(H, pht, s, NZ, NX, NZ);
-  for (int i = 0; i < NZ * NZ; ++i) { s[i] = s[i] + R[i]; si[i] = 0.0; }
-  for (int i = 0; i < NZ; ++i) si[i * NZ + i] = 1.0 / s[i * NZ + i];  // S is diagonal
-  mm(pht, si, k, NX, NZ, NZ);
-  mm(k, y, ky, NX, NZ, 1);
-  for (int i = 0; i < NX; ++i) x[i] = x[i] + ky[i];
-  double ikh[NX * NX], t1[NX * NX], t2[NX * NX], kr[NX * NZ], krk[NX * NX];
-  mm(k, H, ikh, NX, NZ, NX);
-  for (int i = 0; i < NX; ++i)
-    for (int j = 0; j < NX; ++j) ikh[i * NX + j] = ((i == j) ? 1.0 : 0.0) - ikh[i * NX + j];
-  mm(ikh, P, t1, NX, NX, NX);
-  mmt(t1, ikh, t2, NX, NX, NX);
-  mm(k, R, kr, NX, NZ, NZ);
-  mmt(kr, k, krk, NX, NZ, NX);
-  for (int i = 0; i < NX * NX; ++i) P[i] = t2[i] + krk[i];
+__device__ __forceinline__ void kf_correct(double* x, double* P, const double* z) {
+  const double R[NZ] = {1.0, 1.0, 10.0, 10.0};
+  double y[NZ], si[NZ], K[NX * NZ], ikh[NX * NZ];
+#pragma unroll
+  for (int j = 0; j < NZ; ++j) {
+    y[j] = z[j] - x[j];                                   // z - Hx
+    si[j] = 1.0 / (P[j * NX + j] + R[j]);                 // S = HPH' + R is diagonal
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {
+#pragma unroll
+    for (int j = 0; j < NZ; ++j) K[i * NZ + j] = P[i * NX + j] * si[j];   // K = PH' inv(S)
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {                          // x += K y
+    double acc = K[i * NZ + 0] * y[0];
+    acc = acc + K[i * NZ + 1] * y[1];
+    acc = acc + K[i * NZ + 2] * y[2];
+    acc = acc + K[i * NZ + 3] * y[3];
+    x[i] = x[i] + acc;
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {                          // (I - KH)[:, :4]; columns 4..6 are I
+#pragma unroll
+    for (int k = 0; k < NZ; ++k) ikh[i * NZ + k] = ((i == k) ? 1.0 : 0.0) - K[i * NZ + k];
+  }
+  double t1[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {                          // t1 = (I-KH) P
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      double acc = ikh[i * NZ + 0] * P[0 * NX + j];
+      acc = acc + ikh[i * NZ + 1] * P[1 * NX + j];
+      acc = acc + ikh[i * NZ + 2] * P[2 * NX + j];
+      acc = acc + ikh[i * NZ + 3] * P[3 * NX + j];
+      if (i >= NZ) acc = acc + P[i * NX + j];
+      t1[i * NX + j] = acc;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NX; ++i) {                          // P = t1 (I-KH)' + (K R) K'
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      double acc = t1[i * NX + 0] * ikh[j * NZ + 0];
+      acc = acc + t1[i * NX + 1] * ikh[j * NZ + 1];
+      acc = acc + t1[i * NX + 2] * ikh[j * NZ + 2];
+      acc = acc + t1[i * NX + 3] * ikh[j * NZ + 3];
+      if (j >= NZ) acc = acc + t1[i * NX + j];
+      double krk = (K[i * NZ + 0] * R[0]) * K[j * NZ + 0];
+      krk = krk + (K[i * NZ + 1] * R[1]) * K[j * NZ + 1];
+      krk = krk + (K[i * NZ + 2] * R[2]) * K[j * NZ + 2];
+      krk = krk + (K[i * NZ + 3] * R[3]) * K[j * NZ + 3];
+      P[i * NX + j] = acc + krk;
+    }
+  }
 }
 
 __device__ __forceinline__ void box_to_z(const double* b, double* z) {
@@ -131,9 +155,12 @@ __device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no obser
     t.missed += 1;
     return;
   }
+  double x[NX], P[NX * NX];
   if (!t.observed && t.has_frozen) {        // observation-centric re-update
-    for (int i = 0; i < NX; ++i) t.x[i] = t.fx[i];
-    for (int i = 0; i < NX * NX; ++i) t.P[i] = t.fP[i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = t.fx[i];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) P[i] = t.fP[i];
     int gap = t.missed + 1;
     double x1 = t.prev_z[0], y1 = t.prev_z[1], s1 = t.prev_z[2], r1 = t.prev_z[3];
     double w1 = sqrt(s1 * r1), h1 = sqrt(s1 / r1);
@@ -144,21 +171,38 @@ __device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no obser
     for (int i = 0; i < gap; ++i) {
       double w = w1 + (i + 1) * dw, h = h1 + (i + 1) * dh;
       v[0] = x1 + (i + 1) * dx; v[1] = y1 + (i + 1) * dy; v[2] = w * h; v[3] = w / h;
-      kf_correct(t.x, t.P, v);
-      if (i != gap - 1) kf_predict(t.x, t.P);
+      kf_correct(x, P, v);
+      if (i != gap - 1) kf_predict(x, P);
     }
     for (int i = 0; i < NZ; ++i) t.prev_z[i] = v[i];   // history ends with the virtual box
   } else {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) x[i] = t.x[i];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) P[i] = t.P[i];
     for (int i = 0; i < NZ; ++i) t.prev_z[i] = z[i];
   }
   t.observed = 1;
   t.missed = 0;
-  kf_correct(t.x, t.P, z);
+  kf_correct(x, P, z);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) t.x[i] = x[i];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) t.P[i] = P[i];
 }
 
 __device__ void trk_predict(Trk& t, double* box) {
   if (t.x[6] + t.x[2] <= 0) t.x[6] *= 0.0;
-  kf_predict(t.x, t.P);
+  double x[NX], P[NX * NX];
+#pragma unroll
+  for (int i = 0; i < NX; ++i) x[i] = t.x[i];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) P[i] = t.P[i];
+  kf_predict(x, P);
+#pragma unroll
+  for (int i = 0; i < NX; ++i) t.x[i] = x[i];
+#pragma unroll
+  for (int i = 0; i < NX * NX; ++i) t.P[i] = P[i];
   t.age += 1;
   if (t.tsu > 0) t.hit_streak = 0;
   t.tsu += 1;
@@ -392,21 +436,23 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       sh.iou[d * ld + t] = iou_of(sh.dets[d], sh.tbox[t]);
     }
     __syncwarp();
+    int rmax = 0, cmax = 0;                         // max hits per detection / per track
+    for (int d = lane; d < nd; d += 32) {
+      int c = 0;
+      for (int t = 0; t < nt; ++t) c += sh.iou[d * ld + t] > prm.iou_threshold;
+      rmax = max(rmax, c);
+    }
+    for (int t = lane; t < nt; t += 32) {
+      int c = 0;
+      for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > prm.iou_threshold;
+      cmax = max(cmax, c);
+    }
+    rmax = __reduce_max_sync(0xffffffffu, rmax);
+    cmax = __reduce_max_sync(0xffffffffu, cmax);
     if (lane == 0) {
       sh.n_pairs = 0;
       sh.go = 0;                                    // 1: Hungarian needed
       if (nt > 0 && nd > 0) {
-        int rmax = 0, cmax = 0;
-        for (int d = 0; d < nd; ++d) {
-          int c = 0;
-          for (int t = 0; t < nt; ++t) c += sh.iou[d * ld + t] > prm.iou_threshold;
-          rmax = max(rmax, c);
-        }
-        for (int t = 0; t < nt; ++t) {
-          int c = 0;
-          for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > prm.iou_threshold;
-          cmax = max(cmax, c);
-        }
         if (rmax == 1 && cmax == 1) {
           for (int d = 0; d < nd; ++d)
             for (int t = 0; t < nt; ++t)

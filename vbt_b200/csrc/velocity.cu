@@ -227,8 +227,10 @@ __global__ void velocity_update_kernel(Lane* lanes, double* path, double* phases
                                        int32_t* lane_begin, int L, double plate_diameter,
                                        double diff_threshold, double min_distance,
                                        int smooth, int finish) {
-  int l = blockIdx.x * blockDim.x + threadIdx.x;
-  if (l >= L) return;
+  // one lane per CTA (thread 0): lanes are independent serial recurrences that diverge
+  // from one another, so they must not share a warp
+  const int l = blockIdx.x;
+  if (l >= L || threadIdx.x != 0) return;
   Lane s = lanes[l];
   Ctx c;
   c.s = &s;
@@ -363,8 +365,7 @@ int vbt_velocity_update(vbt_velocity* v, const double* dev_rows, const int32_t* 
               "vbt_velocity_update: null pointer");
   VBT_REQUIRE(L > 0 && L <= v->L && row_cap > 0, "vbt_velocity_update: L=%d exceeds lanes=%d", L,
               v->L);
-  // 32 threads per block: lanes are independent serial recurrences, spread them over SMs
-  velocity_update_kernel<<<vbt::ceil_div(L, 32), 32, 0, (cudaStream_t)stream>>>(
+  velocity_update_kernel<<<L, 32, 0, (cudaStream_t)stream>>>(
       v->lanes, v->path, v->phases, v->path_cap, v->phase_cap, dev_rows, dev_row_count, row_cap,
       dev_lane_table, dev_lane_id, dev_lane_begin, L, plate_diameter, diff_threshold,
       min_distance, smooth, finish);

@@ -73,7 +73,10 @@ class Detector:
     def __del__(self):
         h, self.handle = getattr(self, 'handle', None), None
         if h:
-            _lib.lib().vbt_model_destroy(h)
+            try:
+                _lib.lib().vbt_model_destroy(h)
+            except Exception:      # interpreter shutdown: module globals are gone
+                pass
 
     # -- per-op device timing (bench.py) -----------------------------------------------------
     def profile(self, enable=True):

@@ -47,7 +47,10 @@ class BatchedTracker:
     def __del__(self):
         h, self.handle = getattr(self, 'handle', None), None
         if h:
-            _lib.lib().vbt_tracker_destroy(h)
+            try:
+                _lib.lib().vbt_tracker_destroy(h)
+            except Exception:      # interpreter shutdown: module globals are gone
+                pass
 
     def reset(self):
         _lib.check(_lib.lib().vbt_tracker_reset(self.handle, _lib.stream_ptr()))

@@ -74,7 +74,10 @@ class _Lanes:
     def __del__(self):
         h, self.handle = getattr(self, 'handle', None), None
         if h:
-            _lib.lib().vbt_velocity_destroy(h)
+            try:
+                _lib.lib().vbt_velocity_destroy(h)
+            except Exception:      # interpreter shutdown: module globals are gone
+                pass
 
     def reset(self):
         _lib.check(_lib.lib().vbt_velocity_reset(self.handle, _lib.stream_ptr()))
