@@ -43,6 +43,8 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=12, help='frames timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--profiler-range', action='store_true',
+                    help='cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)')
     return ap.parse_args()
 
 
@@ -250,11 +252,17 @@ def main():
     launches0 = _lib.lib().vbt_launch_count()
     frames0 = state['frames']
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     ev0.record()
     for _ in range(args.steps):
         one_step()
     gather_tables()
     ev1.record()
+    if args.profiler_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
@@ -262,6 +270,9 @@ def main():
     launches = _lib.lib().vbt_launch_count() - launches0
     op_ms, calls = det.op_times()
     det.profile(False)
+    # workload statistics of the last timed batch (read after the timed region)
+    dets_per_frame = float(pipe.det_count[0, :B].float().mean().item())
+    live_tracks = int(len(pipe.tracker.peek(0)))
     stage_events, pipe.stage_events = pipe.stage_events, None
     t = torch.tensor([ms], dtype=torch.float64, device='cuda')
     ft = torch.tensor([float(frames)], dtype=torch.float64, device='cuda')
@@ -394,6 +405,7 @@ def main():
                             'frame stride 1',
                 'variant': args.variant, 'batch': B, 'clip_frames': args.clip_frames,
                 'frames_per_timed_region': frames_all, 'videos_finished': state['videos'],
+                'detections_per_frame': dets_per_frame, 'live_tracks': live_tracks,
                 'cache': 'inputs larger than L2: 398 MB of frames per step vs 126 MB L2, no flush needed',
                 'parallelism': f'{world} video shard(s), one per GPU, NCCL gather of row tables at the end',
             },

@@ -1,0 +1,57 @@
+"""Single-kernel parity on a B200: one-op layer programs (tests/micrograph.py) through
+vbt_detect vs oracle/effdet.py, bit-exact int8, at shapes the full networks do not visit
+(K / N / M tails of the tcgen05 pointwise GEMM, multi-chunk K and N, residual epilogue;
+depthwise 3x3 / 5x5 at stride 1 / 2 with odd sizes)."""
+import numpy as np
+import pytest
+
+from oracle import effdet as OE
+import micrograph as MG
+
+pytestmark = pytest.mark.gpu
+
+
+def check(g, B, seed=1):
+    x, xp = MG.random_input(g, B, seed)
+    _, _, want = OE.run(g, x, keep=True)
+    got = MG.run_gpu(g, xp)
+    for op in g.ops:
+        t = g.tensors[op.out]
+        vals, pad = got[op.out]
+        assert np.array_equal(vals.astype(np.int16), want[op.out]), f'{op.name}: values differ'
+        assert np.all(pad == t.zp), f'{op.name}: pad channels must hold the zero point'
+
+
+@pytest.mark.parametrize('h,w,cin,cout,B', [
+    (8, 16, 16, 16, 1),          # one exact 128-row tile, smallest K and N
+    (5, 7, 16, 96, 3),           # M tail (105 rows), b2.0.expand channel shape
+    (9, 9, 24, 144, 2),          # cin pad 24->32
+    (9, 9, 40, 240, 2),          # cin_p 48: odd number of 16-byte K chunks
+    (6, 5, 80, 480, 5),          # N split in two chunks of 240
+    (4, 4, 112, 672, 9),         # N = 3 x 224, K = 7 chunks
+    (3, 3, 192, 1152, 15),       # N = 5 chunks, M tail
+    (3, 3, 1152, 192, 15),       # K = 72 chunks -> 5 K iterations
+    (5, 5, 672, 112, 6),         # K = 42 chunks (last iteration 10)
+    (10, 10, 320, 64, 2),        # BiFPN lateral
+    (7, 3, 272, 48, 7),          # K just over one stage (17 chunks)
+    (40, 40, 64, 64, 3),         # many tiles
+])
+@pytest.mark.parametrize('act', [False, True])
+def test_pointwise(h, w, cin, cout, B, act):
+    check(MG.pw_graph(h, w, cin, cout, act=act, seed=h * 1000 + cin), B)
+
+
+@pytest.mark.parametrize('h,w,c,cmid,B', [(8, 16, 16, 96, 1), (5, 7, 24, 144, 3), (10, 10, 112, 672, 2),
+                                          (4, 4, 192, 1152, 9), (20, 20, 40, 240, 2)])
+def test_pointwise_residual(h, w, c, cmid, B):
+    check(MG.pw_graph(h, w, c, cmid, act=True, residual=True, seed=c), B)
+
+
+@pytest.mark.parametrize('h,w,c,k,stride,B', [
+    (16, 16, 32, 3, 1, 2), (17, 13, 96, 3, 2, 3), (16, 16, 144, 5, 2, 2), (9, 11, 240, 5, 1, 2),
+    (5, 5, 64, 3, 1, 3), (3, 3, 64, 3, 1, 5), (40, 40, 40, 5, 1, 1), (7, 7, 1152, 3, 1, 2),
+    (33, 31, 16, 3, 2, 1), (10, 10, 672, 5, 2, 2),
+])
+@pytest.mark.parametrize('act', [False, True])
+def test_depthwise(h, w, c, k, stride, B, act):
+    check(MG.dw_graph(h, w, c, k, stride, act=act, seed=h * 100 + c), B)

@@ -359,8 +359,11 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(dev_workspace);
   const long long Np = m->hdr.n_anchors_pad;
+  // tensors without a workspace slot (the model input) live in the caller's buffer
   auto tensor_ptr = [&](int id) -> int8_t* {
-    return reinterpret_cast<int8_t*>(ws + (size_t)B * (size_t)m->tensors[id].ws_offset);
+    const int64_t off = m->tensors[id].ws_offset;
+    if (off < 0) return reinterpret_cast<int8_t*>(const_cast<uint8_t*>(dev_in));
+    return reinterpret_cast<int8_t*>(ws + (size_t)B * (size_t)off);
   };
   auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
   int launched = 0;

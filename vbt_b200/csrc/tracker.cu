@@ -346,6 +346,95 @@ __device__ int assign_min_cost(const double* cost, int ld, int n, int m, int* pa
   return cnt;
 }
 
+// Warp-parallel form of assign_min_cost for min(n,m) <= max(n,m) <= 31: lane j owns column
+// j of the (possibly transposed) problem -- v[j], minv[j], way[j], used[j], p[j] live in
+// registers, u[] in shared memory; the column scan of the serial procedure becomes one
+// step per lane plus a warp arg-min that breaks ties towards the lowest column, which is
+// what the serial strict `<` scan does.  Same floating-point expressions, same result.
+// All 32 lanes must call it; returns the pair count (-1: no augmenting column).
+__device__ int assign_min_cost_warp(const double* cost, int ld, int n, int m, int* pair_r, int* pair_c,
+                                    double* u_s /* [32] shared */, int lane) {
+  if (n == 0 || m == 0) return 0;
+  const bool tr = n > m;
+  const int N = tr ? m : n, M = tr ? n : m;
+  const unsigned full = 0xffffffffu;
+  double v = 0.0, minv = INFINITY;
+  int p = 0, way = 0;
+  bool used = false;
+  u_s[lane] = 0.0;
+  __syncwarp();
+  const bool col = lane >= 1 && lane <= M;
+  for (int i = 1; i <= N; ++i) {
+    if (lane == 0) p = i;
+    int j0 = 0;
+    minv = INFINITY;
+    used = false;
+    while (true) {
+      if (lane == j0) used = true;
+      const int i0 = __shfl_sync(full, p, j0);
+      double key = INFINITY;
+      if (col && !used) {
+        const double cij = tr ? cost[(lane - 1) * ld + (i0 - 1)] : cost[(i0 - 1) * ld + (lane - 1)];
+        const double cur = cij - u_s[i0] - v;
+        if (cur < minv) { minv = cur; way = j0; }
+        key = minv;
+      }
+      int j1 = (key < INFINITY) ? lane : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double k2 = __shfl_xor_sync(full, key, o);
+        const int jj = __shfl_xor_sync(full, j1, o);
+        // candidates carry j1 == 0 when their key is not finite-below-inf
+        const bool take = (jj != 0) && (j1 == 0 || k2 < key || (k2 == key && jj < j1));
+        if (take) { key = k2; j1 = jj; }
+      }
+      if (j1 == 0) return -1;
+      const double delta = key;
+      __syncwarp();
+      if (used) {                       // lanes 0..M that are on the alternating tree
+        u_s[p] += delta;                // distinct rows: p is injective over used columns
+        v -= delta;
+      } else if (col) {
+        minv -= delta;
+      }
+      __syncwarp();
+      j0 = j1;
+      if (__shfl_sync(full, p, j0) == 0) break;
+    }
+    while (true) {                      // augment along the way[] chain
+      const int j1 = __shfl_sync(full, way, j0);
+      const int pj1 = __shfl_sync(full, p, j1);
+      if (lane == j0) p = pj1;
+      j0 = j1;
+      if (j0 == 0) break;
+    }
+  }
+  // pairs sorted by row of the ORIGINAL orientation
+  int cnt = 0;
+  if (!tr) {
+    // row i-1 (i = 1..N) is matched to the column whose p == i
+    for (int i = 1; i <= N; ++i) {
+      const unsigned mask = __ballot_sync(full, col && p == i);
+      if (mask) {
+        if (lane == 0) { pair_r[cnt] = i - 1; pair_c[cnt] = __ffs(mask) - 2; }
+        ++cnt;
+      }
+    }
+  } else {
+    for (int j = 1; j <= M; ++j) {
+      const int pj = __shfl_sync(full, p, j);
+      if (pj != 0) {
+        if (lane == 0) { pair_r[cnt] = j - 1; pair_c[cnt] = pj - 1; }
+        ++cnt;
+      }
+    }
+  }
+  __syncwarp();
+  return cnt;
+}
+
+constexpr int kCache = 32;  // track slots 0..kCache-1 are staged in shared memory for the launch
+
 struct Shared {                 // carved from dynamic shared memory, ld = max_tracks
   double (*dets)[6];            // [kMaxD][6]
   double (*tbox)[4];            // [ld][4] predicted boxes, list order
@@ -354,13 +443,17 @@ struct Shared {                 // carved from dynamic shared memory, ld = max_t
   int *pair_d, *pair_t;         // [kMaxD]
   int *un_d, *un_t;             // [kMaxD], [ld]
   unsigned char* nanflag;       // [ld]
+  double u[32];                 // row potentials of the warp-parallel assignment
+  Trk* cache;                   // [kCache] low slots of this video's track table
+  Video* vid;                   // this video's list state
   int ld;
   int n_pairs, n_un_d, n_un_t, nd, nt, go;
 };
 
 __host__ __device__ inline size_t shared_bytes(int ld) {
   return sizeof(double) * (kMaxD * 6 + (size_t)ld * 4 + 2 * (size_t)kMaxD * ld) +
-         sizeof(int) * (3 * kMaxD + (size_t)ld) + (size_t)ld + 16;
+         sizeof(int) * (3 * kMaxD + (size_t)ld) + ((size_t)ld + 15) / 16 * 16 + 16 +
+         sizeof(Trk) * kCache + sizeof(Video);
 }
 
 __global__ void __launch_bounds__(32) tracker_update_kernel(
@@ -381,12 +474,34 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     sh.pair_t = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
     sh.un_d = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
     sh.un_t = reinterpret_cast<int*>(p); p += sizeof(int) * (size_t)max_tracks;
-    sh.nanflag = p;
+    sh.nanflag = p; p += ((size_t)max_tracks + 15) / 16 * 16;
+    sh.cache = reinterpret_cast<Trk*>(p); p += sizeof(Trk) * kCache;
+    sh.vid = reinterpret_cast<Video*>(p);
   }
   __syncwarp();
   const int ld = max_tracks;
-  Video& vid = videos[v];
-  Trk* trk = tracks + (size_t)v * max_tracks;
+  // The recurrence is a chain of dependent accesses to a few KB of state: stage the list
+  // state and the low track slots (births take the lowest free slot) in shared memory
+  // for the whole launch, write them back at the end.
+  static_assert(sizeof(Trk) % 8 == 0 && sizeof(Video) % 4 == 0, "word copies");
+  Video& vid = *sh.vid;
+  Trk* gtrk = tracks + (size_t)v * max_tracks;
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(videos + v);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(sh.vid);
+    for (int i = lane; i < (int)(sizeof(Video) / 4); i += 32) dst[i] = src[i];
+    __syncwarp();
+    constexpr int W = sizeof(Trk) / 8;
+    for (int s = 0; s < kCache && s < max_tracks; ++s) {
+      if (!vid.used[s]) continue;
+      const uint64_t* a = reinterpret_cast<const uint64_t*>(gtrk + s);
+      uint64_t* b = reinterpret_cast<uint64_t*>(sh.cache + s);
+      for (int i = lane; i < W; i += 32) b[i] = a[i];
+    }
+    __syncwarp();
+  }
+  Trk* const cache = sh.cache;
+  auto T = [&](int slot) -> Trk& { return slot < kCache ? cache[slot] : gtrk[slot]; };
   const int nf = min(n_frames[v], F);
   const double vfps = fps[v];
   double* vrows = rows + (size_t)v * row_cap * VBT_ROW_COLS;
@@ -412,7 +527,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     // ---- predict every track (lane-parallel) ---------------------------------------
     for (int t = lane; t < sh.nt; t += 32) {
       double b[4];
-      trk_predict(trk[vid.order[t]], b);
+      trk_predict(T(vid.order[t]), b);
       for (int j = 0; j < 4; ++j) sh.tbox[t][j] = b[j];
       sh.nanflag[t] = (isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3])) ? 1 : 0;
     }
@@ -469,7 +584,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       const double kPi = 3.141592653589793;
       for (int i = lane; i < nd * nt; i += 32) {
         int d = i / nt, t = i % nt;
-        const Trk& tk = trk[vid.order[t]];
+        const Trk& tk = T(vid.order[t]);
         const double* prev = k_previous(tk, prm.delta_t);
         double pb[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
         if (prev) for (int j = 0; j < 5; ++j) pb[j] = prev[j];
@@ -488,9 +603,15 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         sh.cost[d * ld + t] = -(sh.iou[d * ld + t] + angle_cost);
       }
       __syncwarp();
+      int np = 0;
+      if (max(nd, nt) <= 31) {
+        np = assign_min_cost_warp(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t, sh.u, lane);
+      } else if (lane == 0) {
+        np = assign_min_cost(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t);
+      }
       if (lane == 0) {
-        sh.n_pairs = assign_min_cost(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t);
-        if (sh.n_pairs < 0) { sh.n_pairs = 0; vid.status = VBT_EINVAL; }
+        if (np < 0) { np = 0; vid.status = VBT_EINVAL; }
+        sh.n_pairs = np;
       }
       __syncwarp();
     }
@@ -511,14 +632,14 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     }
     __syncwarp();
     for (int i = lane; i < sh.n_pairs; i += 32)
-      trk_update(trk[vid.order[sh.pair_t[i]]], sh.dets[sh.pair_d[i]], prm.delta_t);
+      trk_update(T(vid.order[sh.pair_t[i]]), sh.dets[sh.pair_d[i]], prm.delta_t);
     __syncwarp();
     // ---- second round: unmatched detections vs last observations (DIoU) --------------
     if (sh.n_un_d > 0 && sh.n_un_t > 0) {
       const int a_n = sh.n_un_d, b_n = sh.n_un_t;
       for (int i = lane; i < a_n * b_n; i += 32) {
         int a = i / b_n, b = i % b_n;
-        const Trk& tk = trk[vid.order[sh.un_t[b]]];
+        const Trk& tk = T(vid.order[sh.un_t[b]]);
         sh.cost[a * ld + b] = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
       }
       __syncwarp();
@@ -531,11 +652,20 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
             if (isnan(q)) any_nan = true; else mx = fmax(mx, q);
           }
         sh.n_pairs = 0;
-        if (!any_nan && mx > prm.iou_threshold) {
-          for (int a = 0; a < a_n; ++a)
-            for (int b = 0; b < b_n; ++b) sh.iou[a * ld + b] = -sh.cost[a * ld + b];
-          int pr[kMaxD], pc[kMaxD];
-          int np = assign_min_cost(sh.iou, ld, a_n, b_n, pr, pc);
+        sh.go = (!any_nan && mx > prm.iou_threshold) ? 1 : 0;
+      }
+      __syncwarp();
+      if (sh.go) {
+        for (int i = lane; i < a_n * b_n; i += 32) {
+          int a = i / b_n, b = i % b_n;
+          sh.iou[a * ld + b] = -sh.cost[a * ld + b];
+        }
+        __syncwarp();
+        int pr[kMaxD], pc[kMaxD];
+        int np = 0;
+        if (max(a_n, b_n) <= 31) np = assign_min_cost_warp(sh.iou, ld, a_n, b_n, pr, pc, sh.u, lane);
+        else if (lane == 0) np = assign_min_cost(sh.iou, ld, a_n, b_n, pr, pc);
+        if (lane == 0) {
           if (np < 0) { np = 0; vid.status = VBT_EINVAL; }
           bool rm_d[kMaxD], rm_t[kMaxT];
           for (int a = 0; a < a_n; ++a) rm_d[a] = false;
@@ -561,11 +691,11 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       }
       __syncwarp();
       for (int i = lane; i < sh.n_pairs; i += 32)
-        trk_update(trk[vid.order[sh.pair_t[i]]], sh.dets[sh.pair_d[i]], prm.delta_t);
+        trk_update(T(vid.order[sh.pair_t[i]]), sh.dets[sh.pair_d[i]], prm.delta_t);
       __syncwarp();
     }
     for (int i = lane; i < sh.n_un_t; i += 32)
-      trk_update(trk[vid.order[sh.un_t[i]]], nullptr, prm.delta_t);
+      trk_update(T(vid.order[sh.un_t[i]]), nullptr, prm.delta_t);
     __syncwarp();
     // ---- births, output rows, deaths (lane 0, list order matters) ---------------------
     if (lane == 0) {
@@ -574,7 +704,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         for (int s = 0; s < max_tracks; ++s) if (!vid.used[s]) { slot = s; break; }
         if (slot < 0 || vid.n_tracks >= max_tracks) { vid.status = VBT_ECAPACITY; break; }
         vid.used[slot] = 1;
-        trk_init(trk[slot], sh.dets[sh.un_d[i]], vid.next_id++);
+        trk_init(T(slot), sh.dets[sh.un_d[i]], vid.next_id++);
         vid.order[vid.n_tracks++] = slot;
       }
       const double time = (double)frame_no[(size_t)v * F + f] / vfps;     // track.py:169
@@ -582,7 +712,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       int n_out = 0;
       int rc = row_count[v];
       for (int t = vid.n_tracks - 1; t >= 0; --t) {
-        Trk& tk = trk[vid.order[t]];
+        Trk& tk = T(vid.order[t]);
         double box[4];
         double sum = tk.last_obs[0] + tk.last_obs[1] + tk.last_obs[2] + tk.last_obs[3] + tk.last_obs[4];
         if (!tk.has_last || sum < 0) x_to_box(tk.x, box);
@@ -615,12 +745,25 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       int k = 0;
       for (int t = 0; t < vid.n_tracks; ++t) {
         int slot = vid.order[t];
-        if (trk[slot].tsu > prm.max_age) { vid.used[slot] = 0; continue; }
+        if (T(slot).tsu > prm.max_age) { vid.used[slot] = 0; continue; }
         vid.order[k++] = slot;
       }
       vid.n_tracks = k;
     }
     __syncwarp();
+  }
+  {                                                 // write the staged state back
+    __syncwarp();
+    constexpr int W = sizeof(Trk) / 8;
+    for (int s = 0; s < kCache && s < max_tracks; ++s) {
+      if (!vid.used[s]) continue;
+      const uint64_t* a = reinterpret_cast<const uint64_t*>(sh.cache + s);
+      uint64_t* b = reinterpret_cast<uint64_t*>(gtrk + s);
+      for (int i = lane; i < W; i += 32) b[i] = a[i];
+    }
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sh.vid);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(videos + v);
+    for (int i = lane; i < (int)(sizeof(Video) / 4); i += 32) dst[i] = src[i];
   }
   // a call whose last frame was empty still reports "nothing emitted"
   if (lane == 0 && last_out_count && nf > 0 && det_count[(size_t)v * F + nf - 1] <= 0)
