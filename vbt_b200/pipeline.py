@@ -33,24 +33,34 @@ class VideoPipeline:
         self.id_lanes = id_lanes
         self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
         D = detector.max_det
-        self.dets = t.zeros((1, self.F, D, 6), dtype=t.float64, device='cuda')
-        self.det_count = t.zeros((1, self.F), dtype=t.int32, device='cuda')
-        self.frame_no = t.zeros((1, self.F), dtype=t.int32, device='cuda')
+        # Two slots of tracker inputs: the detector fills slot i while K7/K8 still read slot
+        # i^1 on the side stream (the recurrence over frames is latency-bound on one warp and
+        # must stay off the detector's critical path).
+        self.dets = t.zeros((2, 1, self.F, D, 6), dtype=t.float64, device='cuda')
+        self.det_count = t.zeros((2, 1, self.F), dtype=t.int32, device='cuda')
+        self.frame_no = t.zeros((2, 1, self.F), dtype=t.int32, device='cuda')
+        self.n_frames = t.zeros((2, 1), dtype=t.int32, device='cuda')
         self.d_fps = t.tensor([self.fps], dtype=t.float64, device='cuda')
-        self.n_frames = t.zeros(1, dtype=t.int32, device='cuda')
         self.lane_table = t.zeros(id_lanes, dtype=t.int32, device='cuda')
         self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda')
         self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
+        self.side = t.cuda.Stream()
+        self.det_ready = [t.cuda.Event() for _ in range(2)]
+        self.slot_free = [t.cuda.Event() for _ in range(2)]
+        self.slot = 0
+        self.last_slot = 0
         self.frames_done = 0
         self.stage_events = None      # bench.py: list of per-step event tuples when profiling
 
-    def _mark(self, marks):
+    def _mark(self, marks, stream=None):
         if marks is not None:
             e = self.torch.cuda.Event(enable_timing=True)
-            e.record()
+            e.record(stream)
             marks.append(e)
 
     def reset(self, fps=None):
+        t = self.torch
+        t.cuda.current_stream().wait_stream(self.side)
         if fps is not None:
             self.fps = float(fps)
             self.d_fps.fill_(self.fps)
@@ -58,35 +68,50 @@ class VideoPipeline:
         self.lanes.reset()
         self.lane_begin.zero_()
         self.frames_done = 0
+        self.side.wait_stream(t.cuda.current_stream())
 
-    def process(self, frames, frame_numbers, swap_rb=True, stream=None):
+    def process(self, frames, frame_numbers, swap_rb=True):
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
-        tensor [n] with the 1-based frame_count of each (track.py:161)."""
+        tensor [n] with the 1-based frame_count of each (track.py:161).
+        Detection (K1, network, K6, packing) is enqueued on the current stream; tracking and
+        velocity (K7, K8) follow on `self.side`, overlapping the next batch's detection."""
+        t = self.torch
+        main = t.cuda.current_stream()
         n = frames.shape[0]
         marks = [] if self.stage_events is not None else None
         self._mark(marks)
         det = self.det
-        images = det.preprocess(frames, swap_rb, stream)
+        images = det.preprocess(frames, swap_rb)
         self._mark(marks)
-        det.network(images, stream)
+        det.network(images)
         self._mark(marks)
-        boxes, _, scores, count, _ = det.postprocess(n, score_to_q(self.threshold), stream=stream)
+        boxes, _, scores, count, _ = det.postprocess(n, score_to_q(self.threshold))
         self._mark(marks)
-        sp = _lib.stream_ptr(stream)
+        k = self.slot
+        self.slot ^= 1
+        self.last_slot = k
+        main.wait_event(self.slot_free[k])           # K7 of two batches ago has read slot k
         _lib.check(_lib.lib().vbt_pack_detections(
             boxes.data_ptr(), scores.data_ptr(), count.data_ptr(), n, self.det.max_det,
-            self.threshold, self.dets.data_ptr(), self.det_count.data_ptr(), sp))
-        self.frame_no[0, :n].copy_(frame_numbers, non_blocking=True)
-        self.n_frames.fill_(n)
+            self.threshold, self.dets[k].data_ptr(), self.det_count[k].data_ptr(),
+            _lib.stream_ptr(main)))
+        self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
+        self.n_frames[k].fill_(n)
         self._mark(marks)
-        self.tracker.update(self.dets, self.det_count, self.frame_no, self.d_fps, self.n_frames,
-                            stream=stream)
-        self._mark(marks)
-        self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
-                          self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
-                          self.plate_diameter, self.diff_threshold, self.min_distance,
-                          smooth=True, finish=False)
-        self._mark(marks)
+        self.det_ready[k].record(main)
+        side = self.side
+        side.wait_event(self.det_ready[k])
+        with t.cuda.stream(side):
+            self._mark(marks, side)
+            self.tracker.update(self.dets[k], self.det_count[k], self.frame_no[k], self.d_fps,
+                                self.n_frames[k], stream=side)
+            self._mark(marks, side)
+            self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
+                              self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
+                              self.plate_diameter, self.diff_threshold, self.min_distance,
+                              smooth=True, finish=False)
+            self._mark(marks, side)
+            self.slot_free[k].record(side)
         if marks is not None:
             self.stage_events.append(marks)
         self.frames_done += n
@@ -94,6 +119,7 @@ class VideoPipeline:
     def finish(self):
         """End of video: run end_processing() on every lane, bring results to the host.
         Returns dict(rows=f64[n,8] append order, phases={id: [Phase]}, path={id: float})."""
+        self.torch.cuda.current_stream().wait_stream(self.side)
         self.tracker.check_status()
         self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
                           self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
