@@ -21,12 +21,21 @@ namespace {
 constexpr int kMaxT = 256;  // live tracks per video (compile-time ceiling)
 constexpr int kMaxD = 32;   // detections per frame
 constexpr int NX = 7, NZ = 4;
+constexpr int NP = 13;      // stored covariance entries, see below
 
+// The covariance of this filter never leaves a block structure: P0, Q and R are diagonal,
+// F couples state i only with i+4 (position <- velocity) and H reads states 0..3, so the
+// pairs (0,4), (1,5), (2,6) and the lone state 3 never mix.  Every other entry of the dense
+// 7x7 matrices the oracle multiplies is an exact zero, and adding 0 * finite terms does not
+// change an IEEE sum, so only the 13 in-block entries are stored and updated -- with the
+// SAME operations in the SAME order as the dense k-ascending products (checked bit for bit
+// against oracle/ocsort.py).  Layout: block b in 0..2 (a = b, v = b + 4):
+//   P[4b+0] = P(a,a)  P[4b+1] = P(a,v)  P[4b+2] = P(v,a)  P[4b+3] = P(v,v);  P[12] = P(3,3)
 struct Trk {
   double x[NX];
-  double P[NX * NX];
+  double P[NP];
   double fx[NX];            // state frozen at the first missed frame
-  double fP[NX * NX];
+  double fP[NP];
   double prev_z[NZ];        // measurement the next re-update interpolates from
   double last_obs[5];
   double obs_box[4][5];     // observations of the last ages, slot = age & 3
@@ -48,88 +57,55 @@ struct Params {
   int max_age, min_hits, delta_t, vdc_cls;
 };
 
-// The oracle multiplies dense 7x7 matrices k-ascending.  F = I + shift and H = [I4 0] are
-// 0/1 matrices, so every dense inner product below collapses to the few terms written
-// out here IN THE SAME ORDER; the skipped terms are exact zeros (0 * finite), which do
-// not change an IEEE sum.  Everything is unrolled over constant indices so x and P live
-// in registers.
+// x = F x ; P = F P F' + Q.  Dense form: t = F P adds row v to row a, P' = t F' adds column
+// v to column a, Q lands on the diagonal.
 __device__ __forceinline__ void kf_predict(double* x, double* P) {
-  // x = F x
   x[0] = x[0] + x[4]; x[1] = x[1] + x[5]; x[2] = x[2] + x[6];
-  // t = F P : rows 0..2 pick up rows 4..6
-  double t[NX * NX];
+  const double qa[3] = {1.0, 1.0, 1.0}, qv[3] = {0.01, 0.01, 0.0001};
 #pragma unroll
-  for (int j = 0; j < NX; ++j) {
-#pragma unroll
-    for (int i = 0; i < NX; ++i)
-      t[i * NX + j] = (i < 3) ? P[i * NX + j] + P[(i + 4) * NX + j] : P[i * NX + j];
+  for (int b = 0; b < 3; ++b) {
+    const double t_aa = P[4 * b + 0] + P[4 * b + 2];
+    const double t_av = P[4 * b + 1] + P[4 * b + 3];
+    const double t_va = P[4 * b + 2];
+    const double t_vv = P[4 * b + 3];
+    P[4 * b + 0] = (t_aa + t_av) + qa[b];
+    P[4 * b + 1] = t_av;
+    P[4 * b + 2] = t_va + t_vv;
+    P[4 * b + 3] = t_vv + qv[b];
   }
-  // P = t F^T + Q : columns 0..2 pick up columns 4..6
-  const double q[NX] = {1.0, 1.0, 1.0, 1.0, 0.01, 0.01, 0.0001};
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      double v = (j < 3) ? t[i * NX + j] + t[i * NX + j + 4] : t[i * NX + j];
-      P[i * NX + j] = (i == j) ? v + q[i] : v;
-    }
-  }
+  P[12] = P[12] + 1.0;
 }
 
+// y = z - Hx ; S = HPH' + R (diagonal) ; K = PH' inv(S) as a multiply by the reciprocal ;
+// x += K y ; P = (I-KH) P (I-KH)' + K R K'  (Joseph form), restricted to the blocks.
 __device__ __forceinline__ void kf_correct(double* x, double* P, const double* z) {
   const double R[NZ] = {1.0, 1.0, 10.0, 10.0};
-  double y[NZ], si[NZ], K[NX * NZ], ikh[NX * NZ];
 #pragma unroll
-  for (int j = 0; j < NZ; ++j) {
-    y[j] = z[j] - x[j];                                   // z - Hx
-    si[j] = 1.0 / (P[j * NX + j] + R[j]);                 // S = HPH' + R is diagonal
+  for (int b = 0; b < 3; ++b) {
+    const double Paa = P[4 * b + 0], Pav = P[4 * b + 1], Pva = P[4 * b + 2], Pvv = P[4 * b + 3];
+    const double y = z[b] - x[b];
+    const double si = 1.0 / (Paa + R[b]);
+    const double Ka = Paa * si, Kv = Pva * si;
+    x[b] = x[b] + Ka * y;
+    x[b + 4] = x[b + 4] + Kv * y;
+    const double ia = 1.0 - Ka, iv = 0.0 - Kv;          // (I - KH)(a,a), (I - KH)(v,a)
+    const double t_aa = ia * Paa, t_av = ia * Pav;
+    const double t_va = iv * Paa + Pva, t_vv = iv * Pav + Pvv;
+    const double ra = Ka * R[b], rv = Kv * R[b];
+    P[4 * b + 0] = t_aa * ia + ra * Ka;
+    P[4 * b + 1] = (t_aa * iv + t_av) + ra * Kv;
+    P[4 * b + 2] = t_va * ia + rv * Ka;
+    P[4 * b + 3] = (t_va * iv + t_vv) + rv * Kv;
   }
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {
-#pragma unroll
-    for (int j = 0; j < NZ; ++j) K[i * NZ + j] = P[i * NX + j] * si[j];   // K = PH' inv(S)
-  }
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {                          // x += K y
-    double acc = K[i * NZ + 0] * y[0];
-    acc = acc + K[i * NZ + 1] * y[1];
-    acc = acc + K[i * NZ + 2] * y[2];
-    acc = acc + K[i * NZ + 3] * y[3];
-    x[i] = x[i] + acc;
-  }
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {                          // (I - KH)[:, :4]; columns 4..6 are I
-#pragma unroll
-    for (int k = 0; k < NZ; ++k) ikh[i * NZ + k] = ((i == k) ? 1.0 : 0.0) - K[i * NZ + k];
-  }
-  double t1[NX * NX];
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {                          // t1 = (I-KH) P
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      double acc = ikh[i * NZ + 0] * P[0 * NX + j];
-      acc = acc + ikh[i * NZ + 1] * P[1 * NX + j];
-      acc = acc + ikh[i * NZ + 2] * P[2 * NX + j];
-      acc = acc + ikh[i * NZ + 3] * P[3 * NX + j];
-      if (i >= NZ) acc = acc + P[i * NX + j];
-      t1[i * NX + j] = acc;
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NX; ++i) {                          // P = t1 (I-KH)' + (K R) K'
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      double acc = t1[i * NX + 0] * ikh[j * NZ + 0];
-      acc = acc + t1[i * NX + 1] * ikh[j * NZ + 1];
-      acc = acc + t1[i * NX + 2] * ikh[j * NZ + 2];
-      acc = acc + t1[i * NX + 3] * ikh[j * NZ + 3];
-      if (j >= NZ) acc = acc + t1[i * NX + j];
-      double krk = (K[i * NZ + 0] * R[0]) * K[j * NZ + 0];
-      krk = krk + (K[i * NZ + 1] * R[1]) * K[j * NZ + 1];
-      krk = krk + (K[i * NZ + 2] * R[2]) * K[j * NZ + 2];
-      krk = krk + (K[i * NZ + 3] * R[3]) * K[j * NZ + 3];
-      P[i * NX + j] = acc + krk;
-    }
+  {
+    const double P33 = P[12];
+    const double y = z[3] - x[3];
+    const double si = 1.0 / (P33 + R[3]);
+    const double K3 = P33 * si;
+    x[3] = x[3] + K3 * y;
+    const double i3 = 1.0 - K3;
+    const double t = i3 * P33;
+    P[12] = t * i3 + (K3 * R[3]) * K3;
   }
 }
 
@@ -148,19 +124,19 @@ __device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no obser
   if (!z) {
     if (t.observed) {
       for (int i = 0; i < NX; ++i) t.fx[i] = t.x[i];
-      for (int i = 0; i < NX * NX; ++i) t.fP[i] = t.P[i];
+      for (int i = 0; i < NP; ++i) t.fP[i] = t.P[i];
       t.has_frozen = 1;
     }
     t.observed = 0;
     t.missed += 1;
     return;
   }
-  double x[NX], P[NX * NX];
+  double x[NX], P[NP];
   if (!t.observed && t.has_frozen) {        // observation-centric re-update
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = t.fx[i];
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) P[i] = t.fP[i];
+    for (int i = 0; i < NP; ++i) P[i] = t.fP[i];
     int gap = t.missed + 1;
     double x1 = t.prev_z[0], y1 = t.prev_z[1], s1 = t.prev_z[2], r1 = t.prev_z[3];
     double w1 = sqrt(s1 * r1), h1 = sqrt(s1 / r1);
@@ -179,7 +155,7 @@ __device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no obser
 #pragma unroll
     for (int i = 0; i < NX; ++i) x[i] = t.x[i];
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) P[i] = t.P[i];
+    for (int i = 0; i < NP; ++i) P[i] = t.P[i];
     for (int i = 0; i < NZ; ++i) t.prev_z[i] = z[i];
   }
   t.observed = 1;
@@ -188,21 +164,21 @@ __device__ void kf_update(Trk& t, const double* z) {   // z == nullptr: no obser
 #pragma unroll
   for (int i = 0; i < NX; ++i) t.x[i] = x[i];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) t.P[i] = P[i];
+  for (int i = 0; i < NP; ++i) t.P[i] = P[i];
 }
 
 __device__ void trk_predict(Trk& t, double* box) {
   if (t.x[6] + t.x[2] <= 0) t.x[6] *= 0.0;
-  double x[NX], P[NX * NX];
+  double x[NX], P[NP];
 #pragma unroll
   for (int i = 0; i < NX; ++i) x[i] = t.x[i];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) P[i] = t.P[i];
+  for (int i = 0; i < NP; ++i) P[i] = t.P[i];
   kf_predict(x, P);
 #pragma unroll
   for (int i = 0; i < NX; ++i) t.x[i] = x[i];
 #pragma unroll
-  for (int i = 0; i < NX * NX; ++i) t.P[i] = P[i];
+  for (int i = 0; i < NP; ++i) t.P[i] = P[i];
   t.age += 1;
   if (t.tsu > 0) t.hit_streak = 0;
   t.tsu += 1;
@@ -259,9 +235,9 @@ __device__ void trk_init(Trk& t, const double* det, int id) {
   double z[NZ];
   box_to_z(det, z);
   for (int i = 0; i < NZ; ++i) t.x[i] = z[i];
-  const double p0[NX] = {10.0, 10.0, 10.0, 10.0, 10000.0, 10000.0, 10000.0};
-  for (int i = 0; i < NX * NX; ++i) t.P[i] = 0.0;
-  for (int i = 0; i < NX; ++i) t.P[i * NX + i] = p0[i];
+  for (int i = 0; i < NP; ++i) t.P[i] = 0.0;
+  for (int b = 0; b < 3; ++b) { t.P[4 * b + 0] = 10.0; t.P[4 * b + 3] = 10000.0; }
+  t.P[12] = 10.0;
   t.id = id; t.tsu = 0; t.hits = 0; t.hit_streak = 0; t.age = 0;
   t.conf = det[4]; t.cls = det[5];
   t.has_last = 0; t.has_vel = 0; t.observed = 0; t.has_frozen = 0; t.missed = 0; t.n_obs = 0;
@@ -442,30 +418,39 @@ struct Shared {                 // carved from dynamic shared memory, ld = max_t
   double* cost;                 // [kMaxD][ld]
   int *pair_d, *pair_t;         // [kMaxD]
   int *un_d, *un_t;             // [kMaxD], [ld]
-  unsigned char* nanflag;       // [ld]
-  double u[32];                 // row potentials of the warp-parallel assignment
+  int *pr, *pc;                 // [kMaxD] second-round assignment (positions in un_d / un_t)
+  unsigned char* flag_t;        // [ld]  per-track scratch flags
+  unsigned char* flag_d;        // [kMaxD]
   Trk* cache;                   // [kCache] low slots of this video's track table
   Video* vid;                   // this video's list state
-  int ld;
-  int n_pairs, n_un_d, n_un_t, nd, nt, go;
+  double u[32];                 // row potentials of the warp-parallel assignment
+  int n_pairs, n_un_d, n_un_t;
 };
 
 __host__ __device__ inline size_t shared_bytes(int ld) {
   return sizeof(double) * (kMaxD * 6 + (size_t)ld * 4 + 2 * (size_t)kMaxD * ld) +
-         sizeof(int) * (3 * kMaxD + (size_t)ld) + ((size_t)ld + 15) / 16 * 16 + 16 +
+         sizeof(int) * (5 * kMaxD + (size_t)ld) + ((size_t)ld + 15) / 16 * 16 + kMaxD + 16 +
          sizeof(Trk) * kCache + sizeof(Video);
 }
 
+__device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) - 1u; }
+
+// One warp steps one video through its next frames.  Every list operation of the
+// reference's Python (filtering detections, dropping tracks, building the matched /
+// unmatched index lists, emitting rows in reverse list order, deleting old tracks) is an
+// order-preserving compaction, done here with warp ballots over 32-wide chunks so that no
+// lane ever walks a list alone; only births (rare, order-dependent slot allocation) and
+// the > 31-wide assignment fallback are serial.
 __global__ void __launch_bounds__(32) tracker_update_kernel(
     Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
     const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det, int max_tracks,
     double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ Shared sh;
+  const unsigned full = 0xffffffffu;
   const int v = blockIdx.x, lane = threadIdx.x;
   if (lane == 0) {
     unsigned char* p = dyn_smem;
-    sh.ld = max_tracks;
     sh.dets = reinterpret_cast<double(*)[6]>(p); p += sizeof(double) * kMaxD * 6;
     sh.tbox = reinterpret_cast<double(*)[4]>(p); p += sizeof(double) * 4 * (size_t)max_tracks;
     sh.iou = reinterpret_cast<double*>(p); p += sizeof(double) * (size_t)kMaxD * max_tracks;
@@ -473,8 +458,12 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     sh.pair_d = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
     sh.pair_t = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
     sh.un_d = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
+    sh.pr = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
+    sh.pc = reinterpret_cast<int*>(p); p += sizeof(int) * kMaxD;
     sh.un_t = reinterpret_cast<int*>(p); p += sizeof(int) * (size_t)max_tracks;
-    sh.nanflag = p; p += ((size_t)max_tracks + 15) / 16 * 16;
+    sh.flag_t = p; p += ((size_t)max_tracks + 15) / 16 * 16;
+    sh.flag_d = p; p += kMaxD;
+    p = reinterpret_cast<unsigned char*>(((uintptr_t)p + 15) & ~(uintptr_t)15);
     sh.cache = reinterpret_cast<Trk*>(p); p += sizeof(Trk) * kCache;
     sh.vid = reinterpret_cast<Video*>(p);
   }
@@ -505,253 +494,335 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
   const int nf = min(n_frames[v], F);
   const double vfps = fps[v];
   double* vrows = rows + (size_t)v * row_cap * VBT_ROW_COLS;
+  int rc = row_count[v];
+  int frame_count = vid.frame_count;
+  const double thr = prm.iou_threshold;
+
+  // detections of the next frame are fetched while the current one is processed
+  int nxt_n = 0;
+  double nxt_d[6] = {0, 0, 0, 0, 0, 0};
+  auto fetch = [&](int f) {
+    nxt_n = 0;
+    if (f < nf) {
+      nxt_n = min(det_count[(size_t)v * F + f], max_det);
+      if (lane < nxt_n) {
+        const double* fd = dets + (((size_t)v * F + f) * max_det + lane) * 6;
+#pragma unroll
+        for (int j = 0; j < 6; ++j) nxt_d[j] = fd[j];
+      }
+    }
+  };
+  fetch(0);
 
   for (int f = 0; f < nf; ++f) {
-    const int nd0 = det_count[(size_t)v * F + f];
+    const int nd0 = nxt_n;
+    double d6[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) d6[j] = nxt_d[j];
+    fetch(f + 1);
     if (nd0 <= 0) continue;                         // track.py:180-181
-    const double* fd = dets + ((size_t)v * F + f) * max_det * 6;
-    if (lane == 0) {
-      vid.frame_count += 1;
-      int nd = 0;
-      for (int i = 0; i < nd0 && i < max_det; ++i) {
-        if (fd[i * 6 + 4] > prm.det_thresh) {
-          if (nd >= kMaxD) { vid.status = VBT_ECAPACITY; break; }
-          for (int j = 0; j < 6; ++j) sh.dets[nd][j] = fd[i * 6 + j];
-          ++nd;
+    frame_count += 1;
+    // ---- detections above det_thresh, order kept ---------------------------------------
+    int nd;
+    {
+      const bool keep = lane < nd0 && d6[4] > prm.det_thresh;
+      const unsigned m = __ballot_sync(full, keep);
+      nd = __popc(m);
+      if (keep) {
+        const int pos = __popc(m & lanemask_lt(lane));
+#pragma unroll
+        for (int j = 0; j < 6; ++j) sh.dets[pos][j] = d6[j];
+      }
+    }
+    // ---- predict every track, drop the ones whose box went NaN (list order kept) ---------
+    int nt = vid.n_tracks;
+    {
+      int kept = 0;
+      for (int base = 0; base < nt; base += 32) {
+        const int t = base + lane;
+        const bool valid = t < nt;
+        const int slot = valid ? vid.order[t] : 0;
+        double b[4] = {0, 0, 0, 0};
+        bool bad = false;
+        if (valid) {
+          trk_predict(T(slot), b);
+          bad = isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3]);
         }
+        const unsigned m = __ballot_sync(full, valid && !bad);
+        if (valid && bad) vid.used[slot] = 0;
+        if (valid && !bad) {
+          const int p = kept + __popc(m & lanemask_lt(lane));
+          vid.order[p] = slot;                      // p <= t: never overwrites an unread entry
+#pragma unroll
+          for (int j = 0; j < 4; ++j) sh.tbox[p][j] = b[j];
+        }
+        kept += __popc(m);
+        __syncwarp();
       }
-      sh.nd = nd;
-      sh.nt = vid.n_tracks;
+      nt = kept;
     }
     __syncwarp();
-    // ---- predict every track (lane-parallel) ---------------------------------------
-    for (int t = lane; t < sh.nt; t += 32) {
-      double b[4];
-      trk_predict(T(vid.order[t]), b);
-      for (int j = 0; j < 4; ++j) sh.tbox[t][j] = b[j];
-      sh.nanflag[t] = (isnan(b[0]) || isnan(b[1]) || isnan(b[2]) || isnan(b[3])) ? 1 : 0;
-    }
-    __syncwarp();
-    if (lane == 0) {                                // drop NaN tracks, keep list order
-      int k = 0;
-      for (int t = 0; t < sh.nt; ++t) {
-        int slot = vid.order[t];
-        if (sh.nanflag[t]) { vid.used[slot] = 0; continue; }
-        vid.order[k] = slot;
-        for (int j = 0; j < 4; ++j) sh.tbox[k][j] = sh.tbox[t][j];
-        ++k;
-      }
-      sh.nt = vid.n_tracks = k;
-    }
-    __syncwarp();
-    const int nd = sh.nd, nt = sh.nt;
     // ---- first association round ----------------------------------------------------
     for (int i = lane; i < nd * nt; i += 32) {
-      int d = i / nt, t = i % nt;
+      const int d = i / nt, t = i - d * nt;
       sh.iou[d * ld + t] = iou_of(sh.dets[d], sh.tbox[t]);
     }
     __syncwarp();
-    int rmax = 0, cmax = 0;                         // max hits per detection / per track
-    for (int d = lane; d < nd; d += 32) {
-      int c = 0;
-      for (int t = 0; t < nt; ++t) c += sh.iou[d * ld + t] > prm.iou_threshold;
-      rmax = max(rmax, c);
+    int rmax = 0, cmax = 0, hit_t = -1;             // hits per detection / per track
+    if (lane < nd) {
+      for (int t = 0; t < nt; ++t)
+        if (sh.iou[lane * ld + t] > thr) { ++rmax; hit_t = t; }
     }
     for (int t = lane; t < nt; t += 32) {
       int c = 0;
-      for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > prm.iou_threshold;
+      for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > thr;
       cmax = max(cmax, c);
     }
-    rmax = __reduce_max_sync(0xffffffffu, rmax);
-    cmax = __reduce_max_sync(0xffffffffu, cmax);
-    if (lane == 0) {
-      sh.n_pairs = 0;
-      sh.go = 0;                                    // 1: Hungarian needed
-      if (nt > 0 && nd > 0) {
-        if (rmax == 1 && cmax == 1) {
-          for (int d = 0; d < nd; ++d)
-            for (int t = 0; t < nt; ++t)
-              if (sh.iou[d * ld + t] > prm.iou_threshold) {
-                sh.pair_d[sh.n_pairs] = d; sh.pair_t[sh.n_pairs] = t; ++sh.n_pairs;
-              }
-        } else {
-          sh.go = 1;
+    const int my_hits = rmax;
+    rmax = __reduce_max_sync(full, rmax);
+    cmax = __reduce_max_sync(full, cmax);
+    int n_pairs = 0;
+    if (nt > 0 && nd > 0) {
+      if (rmax == 1 && cmax == 1) {                 // every overlap is unambiguous
+        const bool has = my_hits == 1;
+        const unsigned m = __ballot_sync(full, has);
+        n_pairs = __popc(m);
+        if (has) {
+          const int pos = __popc(m & lanemask_lt(lane));
+          sh.pair_d[pos] = lane; sh.pair_t[pos] = hit_t;
         }
-      }
-    }
-    __syncwarp();
-    if (sh.go) {
-      const double kPi = 3.141592653589793;
-      for (int i = lane; i < nd * nt; i += 32) {
-        int d = i / nt, t = i % nt;
-        const Trk& tk = T(vid.order[t]);
-        const double* prev = k_previous(tk, prm.delta_t);
-        double pb[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
-        if (prev) for (int j = 0; j < 5; ++j) pb[j] = prev[j];
-        double cxd = (sh.dets[d][0] + sh.dets[d][2]) / 2.0, cyd = (sh.dets[d][1] + sh.dets[d][3]) / 2.0;
-        double cxp = (pb[0] + pb[2]) / 2.0, cyp = (pb[1] + pb[3]) / 2.0;
-        double ddx = cxd - cxp, ddy = cyd - cyp;
-        double norm = sqrt(ddx * ddx + ddy * ddy) + 1e-6;
-        ddx = ddx / norm; ddy = ddy / norm;
-        double vy = tk.has_vel ? tk.vel[0] : 0.0, vx = tk.has_vel ? tk.vel[1] : 0.0;
-        double c = vx * ddx + vy * ddy;
-        c = fmin(fmax(c, -1.0), 1.0);
-        double ang = (kPi / 2.0 - fabs(acos(c))) / kPi;
-        double valid = (pb[4] >= 0) ? 1.0 : 0.0;
-        double mult = prm.vdc_cls ? sh.dets[d][5] : sh.dets[d][4];
-        double angle_cost = ((valid * ang) * prm.inertia) * mult;
-        sh.cost[d * ld + t] = -(sh.iou[d * ld + t] + angle_cost);
-      }
-      __syncwarp();
-      int np = 0;
-      if (max(nd, nt) <= 31) {
-        np = assign_min_cost_warp(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t, sh.u, lane);
-      } else if (lane == 0) {
-        np = assign_min_cost(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t);
-      }
-      if (lane == 0) {
-        if (np < 0) { np = 0; vid.status = VBT_EINVAL; }
-        sh.n_pairs = np;
-      }
-      __syncwarp();
-    }
-    if (lane == 0) {       // unmatched lists + low-IoU rejection, upstream order
-      bool md[kMaxD], mt[kMaxT];
-      for (int d = 0; d < nd; ++d) md[d] = false;
-      for (int t = 0; t < nt; ++t) mt[t] = false;
-      for (int i = 0; i < sh.n_pairs; ++i) { md[sh.pair_d[i]] = true; mt[sh.pair_t[i]] = true; }
-      int nud = 0, nut = 0, k = 0;
-      for (int d = 0; d < nd; ++d) if (!md[d]) sh.un_d[nud++] = d;
-      for (int t = 0; t < nt; ++t) if (!mt[t]) sh.un_t[nut++] = t;
-      for (int i = 0; i < sh.n_pairs; ++i) {
-        int d = sh.pair_d[i], t = sh.pair_t[i];
-        if (sh.iou[d * ld + t] < prm.iou_threshold) { sh.un_d[nud++] = d; sh.un_t[nut++] = t; }
-        else { sh.pair_d[k] = d; sh.pair_t[k] = t; ++k; }
-      }
-      sh.n_pairs = k; sh.n_un_d = nud; sh.n_un_t = nut;
-    }
-    __syncwarp();
-    for (int i = lane; i < sh.n_pairs; i += 32)
-      trk_update(T(vid.order[sh.pair_t[i]]), sh.dets[sh.pair_d[i]], prm.delta_t);
-    __syncwarp();
-    // ---- second round: unmatched detections vs last observations (DIoU) --------------
-    if (sh.n_un_d > 0 && sh.n_un_t > 0) {
-      const int a_n = sh.n_un_d, b_n = sh.n_un_t;
-      for (int i = lane; i < a_n * b_n; i += 32) {
-        int a = i / b_n, b = i % b_n;
-        const Trk& tk = T(vid.order[sh.un_t[b]]);
-        sh.cost[a * ld + b] = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
-      }
-      __syncwarp();
-      if (lane == 0) {
-        double mx = -INFINITY;
-        bool any_nan = false;
-        for (int a = 0; a < a_n; ++a)
-          for (int b = 0; b < b_n; ++b) {
-            double q = sh.cost[a * ld + b];
-            if (isnan(q)) any_nan = true; else mx = fmax(mx, q);
-          }
-        sh.n_pairs = 0;
-        sh.go = (!any_nan && mx > prm.iou_threshold) ? 1 : 0;
-      }
-      __syncwarp();
-      if (sh.go) {
-        for (int i = lane; i < a_n * b_n; i += 32) {
-          int a = i / b_n, b = i % b_n;
-          sh.iou[a * ld + b] = -sh.cost[a * ld + b];
+      } else {
+        const double kPi = 3.141592653589793;
+        for (int i = lane; i < nd * nt; i += 32) {
+          const int d = i / nt, t = i - d * nt;
+          const Trk& tk = T(vid.order[t]);
+          const double* prev = k_previous(tk, prm.delta_t);
+          double pb[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
+          if (prev) for (int j = 0; j < 5; ++j) pb[j] = prev[j];
+          double cxd = (sh.dets[d][0] + sh.dets[d][2]) / 2.0, cyd = (sh.dets[d][1] + sh.dets[d][3]) / 2.0;
+          double cxp = (pb[0] + pb[2]) / 2.0, cyp = (pb[1] + pb[3]) / 2.0;
+          double ddx = cxd - cxp, ddy = cyd - cyp;
+          double norm = sqrt(ddx * ddx + ddy * ddy) + 1e-6;
+          ddx = ddx / norm; ddy = ddy / norm;
+          double vy = tk.has_vel ? tk.vel[0] : 0.0, vx = tk.has_vel ? tk.vel[1] : 0.0;
+          double c = vx * ddx + vy * ddy;
+          c = fmin(fmax(c, -1.0), 1.0);
+          double ang = (kPi / 2.0 - fabs(acos(c))) / kPi;
+          double valid = (pb[4] >= 0) ? 1.0 : 0.0;
+          double mult = prm.vdc_cls ? sh.dets[d][5] : sh.dets[d][4];
+          double angle_cost = ((valid * ang) * prm.inertia) * mult;
+          sh.cost[d * ld + t] = -(sh.iou[d * ld + t] + angle_cost);
         }
         __syncwarp();
-        int pr[kMaxD], pc[kMaxD];
         int np = 0;
-        if (max(a_n, b_n) <= 31) np = assign_min_cost_warp(sh.iou, ld, a_n, b_n, pr, pc, sh.u, lane);
-        else if (lane == 0) np = assign_min_cost(sh.iou, ld, a_n, b_n, pr, pc);
-        if (lane == 0) {
-          if (np < 0) { np = 0; vid.status = VBT_EINVAL; }
-          bool rm_d[kMaxD], rm_t[kMaxT];
-          for (int a = 0; a < a_n; ++a) rm_d[a] = false;
-          for (int b = 0; b < b_n; ++b) rm_t[b] = false;
-          int k = 0;
-          for (int i = 0; i < np; ++i) {
-            if (sh.cost[pr[i] * ld + pc[i]] < prm.iou_threshold) continue;
-            sh.pair_d[k] = sh.un_d[pr[i]]; sh.pair_t[k] = sh.un_t[pc[i]]; ++k;
-            rm_d[pr[i]] = true; rm_t[pc[i]] = true;
-          }
-          sh.n_pairs = k;
-          // np.setdiff1d: sorted unique remainder
-          int nud = 0, nut = 0;
-          bool keep_d[kMaxD], keep_t[kMaxT];
-          for (int d = 0; d < nd; ++d) keep_d[d] = false;
-          for (int t = 0; t < nt; ++t) keep_t[t] = false;
-          for (int a = 0; a < a_n; ++a) if (!rm_d[a]) keep_d[sh.un_d[a]] = true;
-          for (int b = 0; b < b_n; ++b) if (!rm_t[b]) keep_t[sh.un_t[b]] = true;
-          for (int d = 0; d < nd; ++d) if (keep_d[d]) sh.un_d[nud++] = d;
-          for (int t = 0; t < nt; ++t) if (keep_t[t]) sh.un_t[nut++] = t;
-          sh.n_un_d = nud; sh.n_un_t = nut;
+        if (max(nd, nt) <= 31) {
+          np = assign_min_cost_warp(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t, sh.u, lane);
+        } else {
+          if (lane == 0) np = assign_min_cost(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t);
+          np = __shfl_sync(full, np, 0);
         }
+        if (np < 0) { np = 0; if (lane == 0) vid.status = VBT_EINVAL; }
+        n_pairs = np;
+      }
+    }
+    __syncwarp();
+    // ---- unmatched lists (ascending), then pairs below the IoU threshold are undone and
+    //      appended to both lists in pair order (upstream behaviour) ------------------------
+    int n_un_d = 0, n_un_t = 0;
+    {
+      for (int t = lane; t < nt; t += 32) sh.flag_t[t] = 0;
+      if (lane < kMaxD) sh.flag_d[lane] = 0;
+      __syncwarp();
+      int pd = 0, pt = 0;
+      bool rej = false;
+      if (lane < n_pairs) {
+        pd = sh.pair_d[lane]; pt = sh.pair_t[lane];
+        sh.flag_d[pd] = 1; sh.flag_t[pt] = 1;
+        rej = sh.iou[pd * ld + pt] < thr;
       }
       __syncwarp();
-      for (int i = lane; i < sh.n_pairs; i += 32)
-        trk_update(T(vid.order[sh.pair_t[i]]), sh.dets[sh.pair_d[i]], prm.delta_t);
+      {
+        const bool un = lane < nd && !sh.flag_d[lane];
+        const unsigned m = __ballot_sync(full, un);
+        if (un) sh.un_d[__popc(m & lanemask_lt(lane))] = lane;
+        n_un_d = __popc(m);
+      }
+      for (int base = 0; base < nt; base += 32) {
+        const int t = base + lane;
+        const bool un = t < nt && !sh.flag_t[t];
+        const unsigned m = __ballot_sync(full, un);
+        if (un) sh.un_t[n_un_t + __popc(m & lanemask_lt(lane))] = t;
+        n_un_t += __popc(m);
+      }
+      const unsigned mr = __ballot_sync(full, rej);
+      const unsigned mk = __ballot_sync(full, lane < n_pairs && !rej);
       __syncwarp();
+      if (rej) {
+        const int pos = __popc(mr & lanemask_lt(lane));
+        sh.un_d[n_un_d + pos] = pd; sh.un_t[n_un_t + pos] = pt;
+      } else if (lane < n_pairs) {
+        const int pos = __popc(mk & lanemask_lt(lane));
+        sh.pair_d[pos] = pd; sh.pair_t[pos] = pt;
+      }
+      n_un_d += __popc(mr); n_un_t += __popc(mr);
+      n_pairs = __popc(mk);
     }
-    for (int i = lane; i < sh.n_un_t; i += 32)
+    __syncwarp();
+    if (lane < n_pairs) trk_update(T(vid.order[sh.pair_t[lane]]), sh.dets[sh.pair_d[lane]], prm.delta_t);
+    __syncwarp();
+    // ---- second round: unmatched detections vs last observations (DIoU) --------------
+    if (n_un_d > 0 && n_un_t > 0) {
+      const int a_n = n_un_d, b_n = n_un_t;
+      double mx = -INFINITY;
+      bool any_nan = false;
+      for (int i = lane; i < a_n * b_n; i += 32) {
+        const int a = i / b_n, b = i - a * b_n;
+        const Trk& tk = T(vid.order[sh.un_t[b]]);
+        const double q = diou_of(sh.dets[sh.un_d[a]], tk.last_obs);   // [-1]*5 when unseen
+        sh.cost[a * ld + b] = q;
+        sh.iou[a * ld + b] = -q;
+        if (isnan(q)) any_nan = true; else mx = fmax(mx, q);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(full, mx, o));
+      any_nan = __any_sync(full, any_nan);
+      __syncwarp();
+      if (!any_nan && mx > thr) {
+        int np = 0;
+        if (max(a_n, b_n) <= 31) {
+          np = assign_min_cost_warp(sh.iou, ld, a_n, b_n, sh.pr, sh.pc, sh.u, lane);
+        } else {
+          if (lane == 0) np = assign_min_cost(sh.iou, ld, a_n, b_n, sh.pr, sh.pc);
+          np = __shfl_sync(full, np, 0);
+        }
+        if (np < 0) { np = 0; if (lane == 0) vid.status = VBT_EINVAL; }
+        __syncwarp();
+        // accepted pairs in assignment order; the rest stays unmatched, as sorted sets
+        for (int t = lane; t < nt; t += 32) sh.flag_t[t] = 0;
+        if (lane < kMaxD) sh.flag_d[lane] = 0;
+        __syncwarp();
+        bool acc = false;
+        int ad = 0, at = 0;
+        if (lane < np) {
+          const int pa = sh.pr[lane], pb = sh.pc[lane];
+          acc = !(sh.cost[pa * ld + pb] < thr);
+          ad = sh.un_d[pa]; at = sh.un_t[pb];
+        }
+        const unsigned ma = __ballot_sync(full, acc);
+        if (acc) {
+          const int pos = __popc(ma & lanemask_lt(lane));
+          sh.pair_d[pos] = ad; sh.pair_t[pos] = at;
+        }
+        n_pairs = __popc(ma);
+        // keep flags, indexed by detection / track: unmatched entries that were not accepted
+        __syncwarp();
+        if (lane < a_n) sh.flag_d[sh.un_d[lane]] = 1;
+        for (int b = lane; b < b_n; b += 32) sh.flag_t[sh.un_t[b]] = 1;
+        __syncwarp();
+        if (acc) { sh.flag_d[ad] = 0; sh.flag_t[at] = 0; }
+        __syncwarp();
+        {
+          const bool un = lane < nd && sh.flag_d[lane];
+          const unsigned m = __ballot_sync(full, un);
+          __syncwarp();
+          if (un) sh.un_d[__popc(m & lanemask_lt(lane))] = lane;
+          n_un_d = __popc(m);
+        }
+        n_un_t = 0;
+        for (int base = 0; base < nt; base += 32) {
+          const int t = base + lane;
+          const bool un = t < nt && sh.flag_t[t];
+          const unsigned m = __ballot_sync(full, un);
+          if (un) sh.un_t[n_un_t + __popc(m & lanemask_lt(lane))] = t;   // position <= t
+          n_un_t += __popc(m);
+        }
+        __syncwarp();
+        if (lane < n_pairs) trk_update(T(vid.order[sh.pair_t[lane]]), sh.dets[sh.pair_d[lane]], prm.delta_t);
+        __syncwarp();
+      }
+    }
+    for (int i = lane; i < n_un_t; i += 32)
       trk_update(T(vid.order[sh.un_t[i]]), nullptr, prm.delta_t);
     __syncwarp();
-    // ---- births, output rows, deaths (lane 0, list order matters) ---------------------
-    if (lane == 0) {
-      for (int i = 0; i < sh.n_un_d; ++i) {
-        int slot = -1;
-        for (int s = 0; s < max_tracks; ++s) if (!vid.used[s]) { slot = s; break; }
-        if (slot < 0 || vid.n_tracks >= max_tracks) { vid.status = VBT_ECAPACITY; break; }
-        vid.used[slot] = 1;
-        trk_init(T(slot), sh.dets[sh.un_d[i]], vid.next_id++);
-        vid.order[vid.n_tracks++] = slot;
+    // ---- births (slot allocation is order dependent: one lane) -----------------------------
+    if (n_un_d > 0) {
+      if (lane == 0) {
+        for (int i = 0; i < n_un_d; ++i) {
+          int slot = -1;
+          for (int s = 0; s < max_tracks; ++s) if (!vid.used[s]) { slot = s; break; }
+          if (slot < 0 || nt >= max_tracks) { vid.status = VBT_ECAPACITY; break; }
+          vid.used[slot] = 1;
+          trk_init(T(slot), sh.dets[sh.un_d[i]], vid.next_id++);
+          vid.order[nt++] = slot;
+        }
       }
+      nt = __shfl_sync(full, nt, 0);
+      __syncwarp();
+    }
+    // ---- output rows in reverse list order, then deaths -------------------------------------
+    {
       const double time = (double)frame_no[(size_t)v * F + f] / vfps;     // track.py:169
       const bool last_frame = (f == nf - 1);
       int n_out = 0;
-      int rc = row_count[v];
-      for (int t = vid.n_tracks - 1; t >= 0; --t) {
-        Trk& tk = T(vid.order[t]);
-        double box[4];
-        double sum = tk.last_obs[0] + tk.last_obs[1] + tk.last_obs[2] + tk.last_obs[3] + tk.last_obs[4];
-        if (!tk.has_last || sum < 0) x_to_box(tk.x, box);
-        else for (int j = 0; j < 4; ++j) box[j] = tk.last_obs[j];
-        if (tk.tsu < 1 && (tk.hit_streak >= prm.min_hits || vid.frame_count <= prm.min_hits)) {
-          if (rc >= row_cap) {
+      for (int top = nt - 1; top >= 0; top -= 32) {
+        const int t = top - lane;
+        bool emit = false;
+        double box[4] = {0, 0, 0, 0}, dxy[2] = {0, 0}, cc[2] = {0, 0};
+        int id = 0;
+        if (t >= 0) {
+          const Trk& tk = T(vid.order[t]);
+          emit = tk.tsu < 1 && (tk.hit_streak >= prm.min_hits || frame_count <= prm.min_hits);
+          if (emit) {
+            const double sum = tk.last_obs[0] + tk.last_obs[1] + tk.last_obs[2] + tk.last_obs[3] + tk.last_obs[4];
+            if (!tk.has_last || sum < 0) x_to_box(tk.x, box);
+            else for (int j = 0; j < 4; ++j) box[j] = tk.last_obs[j];
+            dxy[0] = tk.x[4]; dxy[1] = tk.x[5]; cc[0] = tk.cls; cc[1] = tk.conf; id = tk.id + 1;
+          }
+        }
+        const unsigned m = __ballot_sync(full, emit);
+        if (emit) {
+          const int pos = __popc(m & lanemask_lt(lane));
+          if (rc + pos >= row_cap) {
             vid.status = VBT_ECAPACITY;
           } else {
-            double* r = vrows + (size_t)rc * VBT_ROW_COLS;
-            r[0] = (double)(tk.id + 1);
+            double* r = vrows + (size_t)(rc + pos) * VBT_ROW_COLS;
+            r[0] = (double)id;
             r[1] = time;
             r[2] = (box[0] + box[2]) / 2;          // odt.py:43-50
             r[3] = (box[1] + box[3]) / 2;
-            r[4] = tk.x[4];                        // track.py:199
-            r[5] = tk.x[5];
+            r[4] = dxy[0];                         // track.py:199
+            r[5] = dxy[1];
             r[6] = fabs(box[3] - box[1]);          // odt.py:32-40
             r[7] = fabs(box[2] - box[0]);          // odt.py:22-29
-            ++rc;
           }
-          if (last_out && last_frame && n_out < max_det) {
-            double* o = last_out + ((size_t)v * max_det + n_out) * 9;
+          if (last_out && last_frame && n_out + pos < max_det) {
+            double* o = last_out + ((size_t)v * max_det + n_out + pos) * 9;
             o[0] = box[0]; o[1] = box[1]; o[2] = box[2]; o[3] = box[3];
-            o[4] = (double)(tk.id + 1); o[5] = tk.cls; o[6] = tk.conf; o[7] = tk.x[4]; o[8] = tk.x[5];
+            o[4] = (double)id; o[5] = cc[0]; o[6] = cc[1]; o[7] = dxy[0]; o[8] = dxy[1];
           }
-          ++n_out;
         }
+        const int c = __popc(m);
+        rc = min(rc + c, row_cap);
+        n_out += c;
       }
-      row_count[v] = rc;
-      if (last_out_count && last_frame) last_out_count[v] = min(n_out, max_det);
-      int k = 0;
-      for (int t = 0; t < vid.n_tracks; ++t) {
-        int slot = vid.order[t];
-        if (T(slot).tsu > prm.max_age) { vid.used[slot] = 0; continue; }
-        vid.order[k++] = slot;
+      if (last_out_count && last_frame && lane == 0) last_out_count[v] = min(n_out, max_det);
+      int kept = 0;
+      for (int base = 0; base < nt; base += 32) {
+        const int t = base + lane;
+        const bool valid = t < nt;
+        const int slot = valid ? vid.order[t] : 0;
+        const bool dead = valid && T(slot).tsu > prm.max_age;
+        const unsigned m = __ballot_sync(full, valid && !dead);
+        if (dead) vid.used[slot] = 0;
+        if (valid && !dead) vid.order[kept + __popc(m & lanemask_lt(lane))] = slot;
+        kept += __popc(m);
+        __syncwarp();
       }
-      vid.n_tracks = k;
+      if (lane == 0) vid.n_tracks = kept;
     }
     __syncwarp();
   }
+  if (lane == 0) { vid.frame_count = frame_count; row_count[v] = rc; }
   {                                                 // write the staged state back
     __syncwarp();
     constexpr int W = sizeof(Trk) / 8;
