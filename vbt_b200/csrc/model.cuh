@@ -10,7 +10,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 2;
+constexpr int kBlobVersion = 3;
 
 struct BlobHeader {
   uint32_t magic;

@@ -16,6 +16,7 @@
 // This file holds the SIMT kernels (stem, depthwise, fusion, pooling, and a dp4a
 // pointwise kernel used for shapes the tcgen05 GEMM in pw_umma.cu does not take).
 #include "model.cuh"
+#include "requant.cuh"
 
 namespace vbt {
 cudaEvent_t* profile_begin(vbt_model* m);
@@ -38,26 +39,37 @@ __device__ __forceinline__ int s8(uint32_t word, int i) {
 }
 
 // ---------------------------------------------------------------------------------------
-// stem: 3x3 stride-2 conv on the uint8 frame, 3 -> 32 channels, ReLU6 clamp
+// stem: 3x3 stride-2 conv on the uint8 frame, 3 -> 32 channels, ReLU6 clamp.
+// One thread = one output pixel x all output channels.  The 3x3 RGB window becomes nine
+// (r,g,b,0) words; weights are stored the same way ([9][cout_p] words), so one
+// dp4a.u32.s32 covers one pixel tap of one output channel.
 // ---------------------------------------------------------------------------------------
 struct StemArgs {
   const uint8_t* in; int8_t* out;
-  const int8_t* w; const int32_t* bias; const float* mult;   // w [cout_p][28]
-  int B, H, W, Ho, Wo, cout_p, pad_top, pad_left, zp_in, zp_out, lo, hi;
+  const uint32_t* w; const int32_t* bias; const float* mult;   // w [9][cout_p]
+  int B, H, W, Ho, Wo, cout_p, pad_top, pad_left, zp_in;
+  vbt::Requant rq;
 };
 
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
 __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
-  __shared__ int8_t sw[64 * 28];
-  __shared__ int32_t sb[64];
-  __shared__ float sm[64];
-  for (int i = threadIdx.x; i < a.cout_p * 28; i += blockDim.x) sw[i] = a.w[i];
+  __shared__ __align__(16) uint32_t sw[9 * 64];
+  __shared__ __align__(16) int32_t sb[64];
+  __shared__ __align__(16) float sm[64];
+  for (int i = threadIdx.x; i < a.cout_p * 9; i += blockDim.x) sw[i] = a.w[i];
   for (int i = threadIdx.x; i < a.cout_p; i += blockDim.x) { sb[i] = a.bias[i]; sm[i] = a.mult[i]; }
   __syncthreads();
   const long long total = (long long)a.B * a.Ho * a.Wo;
+  const uint32_t zpix = (uint32_t)a.zp_in * 0x010101u;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
        p += (long long)gridDim.x * blockDim.x) {
     const int ox = (int)(p % a.Wo), oy = (int)((p / a.Wo) % a.Ho), b = (int)(p / ((long long)a.Wo * a.Ho));
-    int x[27];
+    uint32_t x[9];
     const uint8_t* fin = a.in + (size_t)b * a.H * a.W * 3;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -65,23 +77,39 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = ox * 2 - a.pad_left + kx;
-        const bool in = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W;
-        const uint8_t* px = fin + ((size_t)iy * a.W + ix) * 3;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) x[(ky * 3 + kx) * 3 + c] = in ? (int)__ldg(px + c) : a.zp_in;
+        uint32_t v = zpix;
+        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) {
+          const uint8_t* px = fin + ((size_t)iy * a.W + ix) * 3;
+          v = (uint32_t)__ldg(px) | ((uint32_t)__ldg(px + 1) << 8) | ((uint32_t)__ldg(px + 2) << 16);
+        }
+        x[ky * 3 + kx] = v;
       }
     }
     int8_t* o = a.out + (size_t)p * a.cout_p;
     for (int c0 = 0; c0 < a.cout_p; c0 += 16) {
-      uint32_t packed[4] = {0, 0, 0, 0};
+      int acc[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int c = c0 + j;
-        int acc = sb[c];
+      for (int q = 0; q < 4; ++q) {
+        const int4 bv = *reinterpret_cast<const int4*>(sb + c0 + q * 4);
+        acc[q * 4 + 0] = bv.x; acc[q * 4 + 1] = bv.y; acc[q * 4 + 2] = bv.z; acc[q * 4 + 3] = bv.w;
+      }
 #pragma unroll
-        for (int t = 0; t < 27; ++t) acc += x[t] * (int)sw[c * 28 + t];
-        const int y = requant(acc, sm[c], a.zp_out, a.lo, a.hi);
-        packed[j >> 2] |= (uint32_t)(y & 0xff) << (8 * (j & 3));
+      for (int t = 0; t < 9; ++t) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const uint4 wv = *reinterpret_cast<const uint4*>(sw + t * a.cout_p + c0 + q * 4);
+          acc[q * 4 + 0] = dp4a_us(x[t], wv.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = dp4a_us(x[t], wv.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = dp4a_us(x[t], wv.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = dp4a_us(x[t], wv.w, acc[q * 4 + 3]);
+        }
+      }
+      uint32_t packed[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 mv = *reinterpret_cast<const float4*>(sm + c0 + q * 4);
+        packed[q] = vbt::pack4_s8(a.rq(acc[q * 4 + 0], mv.x), a.rq(acc[q * 4 + 1], mv.y),
+                                  a.rq(acc[q * 4 + 2], mv.z), a.rq(acc[q * 4 + 3], mv.w));
       }
       *reinterpret_cast<uint4*>(o + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
@@ -89,69 +117,110 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// depthwise kxk (k = 3 or 5, stride 1 or 2, TF-SAME): one thread = one output pixel x 16
-// channels (one 128-bit load per tap)
+// depthwise KxK (K = 3 or 5, stride 1 or 2, TF-SAME).  One thread = PX consecutive output
+// pixels of one row x 16 channels.  Weights are pre-masked 32-bit words (channel c in byte
+// c % 4, see effdet.pack_blob), so a tap is 16 dp4a on the four activation words of the
+// pixel with no byte unpacking; the (PX-1)*S+K input columns of a row are loaded once
+// (128-bit) and shared by the PX outputs.  Channel groups vary fastest across threads, so
+// a warp reads whole 128-byte lines.
 // ---------------------------------------------------------------------------------------
 struct DwArgs {
   const int8_t* in; int8_t* out;
-  const int8_t* w; const int32_t* bias; const float* mult;   // w [k*k][c_p]
-  int B, H, W, Ho, Wo, c_p, k, stride, pad_top, pad_left, zp_in, zp_out, lo, hi;
+  const uint32_t* w; const int32_t* bias; const float* mult;   // w [k*k][c_p] masked words
+  int B, H, W, Ho, Wo, c_p, pad_top, pad_left, zp_in;
+  vbt::Requant rq;
 };
 
-template <int K>
-__global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
+template <int K, int S, int PX>
+__global__ void __launch_bounds__(128) dw_kernel(DwArgs a) {
+  constexpr int NCOL = (PX - 1) * S + K;
   const int groups = a.c_p >> 4;
-  const long long total = (long long)a.B * a.Ho * a.Wo * groups;
+  const int xb_n = (a.Wo + PX - 1) / PX;
+  const long long total = (long long)a.B * a.Ho * xb_n * groups;
   const uint32_t zpw = (uint32_t)(a.zp_in & 0xff) * 0x01010101u;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int gidx = (int)(i % groups);
-    const long long p = i / groups;
-    const int ox = (int)(p % a.Wo), oy = (int)((p / a.Wo) % a.Ho), b = (int)(p / ((long long)a.Wo * a.Ho));
-    const int c0 = gidx << 4;
-    int acc[16];
+    long long r = i / groups;
+    const int xb = (int)(r % xb_n); r /= xb_n;
+    const int oy = (int)(r % a.Ho), b = (int)(r / a.Ho);
+    const int c0 = gidx << 4, ox0 = xb * PX;
+    int acc[PX][16];
     {
       const int4* bp = reinterpret_cast<const int4*>(a.bias + c0);
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int4 v = __ldg(bp + q);
-        acc[q * 4 + 0] = v.x; acc[q * 4 + 1] = v.y; acc[q * 4 + 2] = v.z; acc[q * 4 + 3] = v.w;
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          acc[p][q * 4 + 0] = v.x; acc[p][q * 4 + 1] = v.y; acc[p][q * 4 + 2] = v.z; acc[p][q * 4 + 3] = v.w;
+        }
       }
     }
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.c_p + c0;
+    const int ix0 = ox0 * S - a.pad_left;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
-      const int iy = oy * a.stride - a.pad_top + ky;
+      const int iy = oy * S - a.pad_top + ky;
+      const bool row_ok = iy >= 0 && iy < a.H;
+      uint4 col[NCOL];
+#pragma unroll
+      for (int j = 0; j < NCOL; ++j) {
+        const int ix = ix0 + j;
+        col[j] = make_uint4(zpw, zpw, zpw, zpw);
+        if (row_ok && ix >= 0 && ix < a.W)
+          col[j] = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.c_p));
+      }
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const int ix = ox * a.stride - a.pad_left + kx;
-        uint4 xv = make_uint4(zpw, zpw, zpw, zpw);
-        if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W)
-          xv = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.c_p));
-        const uint4 wv = __ldg(reinterpret_cast<const uint4*>(a.w + (size_t)(ky * K + kx) * a.c_p + c0));
-        const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-        const uint32_t ws[4] = {wv.x, wv.y, wv.z, wv.w};
+        const uint4* wp = reinterpret_cast<const uint4*>(a.w + (size_t)(ky * K + kx) * a.c_p + c0);
+        uint4 wv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) wv[q] = __ldg(wp + q);
+#pragma unroll
+        for (int p = 0; p < PX; ++p) {
+          const uint4 xv = col[p * S + kx];
+          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            acc[p][q * 4 + 0] = __dp4a((int)xs[q], (int)wv[q].x, acc[p][q * 4 + 0]);
+            acc[p][q * 4 + 1] = __dp4a((int)xs[q], (int)wv[q].y, acc[p][q * 4 + 1]);
+            acc[p][q * 4 + 2] = __dp4a((int)xs[q], (int)wv[q].z, acc[p][q * 4 + 2]);
+            acc[p][q * 4 + 3] = __dp4a((int)xs[q], (int)wv[q].w, acc[p][q * 4 + 3]);
+          }
+        }
+      }
+    }
+    float ms[16];
+    {
+      const float4* mp = reinterpret_cast<const float4*>(a.mult + c0);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 mv = __ldg(mp + q);
+        ms[q * 4 + 0] = mv.x; ms[q * 4 + 1] = mv.y; ms[q * 4 + 2] = mv.z; ms[q * 4 + 3] = mv.w;
+      }
+    }
+    int8_t* orow = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox0) * a.c_p + c0;
+#pragma unroll
+    for (int p = 0; p < PX; ++p) {
+      if (ox0 + p < a.Wo) {
+        uint32_t packed[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[q * 4 + j] += s8(xs[q], j) * s8(ws[q], j);
+          packed[q] = vbt::pack4_s8(a.rq(acc[p][q * 4 + 0], ms[q * 4 + 0]), a.rq(acc[p][q * 4 + 1], ms[q * 4 + 1]),
+                                    a.rq(acc[p][q * 4 + 2], ms[q * 4 + 2]), a.rq(acc[p][q * 4 + 3], ms[q * 4 + 3]));
+        *reinterpret_cast<uint4*>(orow + (size_t)p * a.c_p) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       }
     }
-    uint32_t packed[4] = {0, 0, 0, 0};
-    const float4* mp = reinterpret_cast<const float4*>(a.mult + c0);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float4 mv = __ldg(mp + q);
-      const float ms[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int y = requant(acc[q * 4 + j], ms[j], a.zp_out, a.lo, a.hi);
-        packed[q] |= (uint32_t)(y & 0xff) << (8 * j);
-      }
-    }
-    *reinterpret_cast<uint4*>(a.out + (size_t)p * a.c_p + c0) =
-        make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
+}
+
+template <int K, int S, int PX>
+void launch_dw(const DwArgs& a, cudaStream_t st) {
+  const long long items = (long long)a.B * a.Ho * ((a.Wo + PX - 1) / PX) * (a.c_p / 16);
+  long long g = (items + 127) / 128;
+  const long long cap = 148LL * 32;
+  dw_kernel<K, S, PX><<<(int)(g < 1 ? 1 : (g > cap ? cap : g)), 128, 0, st>>>(a);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -374,12 +443,12 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
       case OP_STEM: {
         StemArgs a;
         a.in = dev_in; a.out = tensor_ptr(op.out);
-        a.w = reinterpret_cast<const int8_t*>(data(op.w_off));
+        a.w = reinterpret_cast<const uint32_t*>(data(op.w_off));
         a.bias = reinterpret_cast<const int32_t*>(data(op.bias_off));
         a.mult = reinterpret_cast<const float*>(data(op.scale_off));
         a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out;
         a.cout_p = op.cout_p; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
-        a.zp_in = op.zp_in[0]; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
+        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
         VBT_REQUIRE(op.cout_p <= 64 && op.k == 3 && op.stride == 2, "vbt_detect: unsupported stem");
         stem_kernel<<<grid_for((long long)B * op.h_out * op.w_out, 128), 128, 0, st>>>(a);
         break;
@@ -387,16 +456,18 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
       case OP_DW: {
         DwArgs a;
         a.in = tensor_ptr(op.in[0]); a.out = tensor_ptr(op.out);
-        a.w = reinterpret_cast<const int8_t*>(data(op.w_off));
+        a.w = reinterpret_cast<const uint32_t*>(data(op.w_off));
         a.bias = reinterpret_cast<const int32_t*>(data(op.bias_off));
         a.mult = reinterpret_cast<const float*>(data(op.scale_off));
         a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out; a.c_p = op.cout_p;
-        a.k = op.k; a.stride = op.stride; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
-        a.zp_in = op.zp_in[0]; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
-        const int grid = grid_for((long long)B * op.h_out * op.w_out * (op.cout_p / 16), 256);
-        if (op.k == 3) dw_kernel<3><<<grid, 256, 0, st>>>(a);
-        else if (op.k == 5) dw_kernel<5><<<grid, 256, 0, st>>>(a);
-        else VBT_REQUIRE(false, "vbt_detect: depthwise kernel size %d", op.k);
+        a.pad_top = op.pad_top; a.pad_left = op.pad_left;
+        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
+        const bool wide = op.w_out >= 8;          // tiny levels: one pixel per thread
+        if (op.k == 3 && op.stride == 1) { if (wide) launch_dw<3, 1, 4>(a, st); else launch_dw<3, 1, 1>(a, st); }
+        else if (op.k == 3 && op.stride == 2) { if (wide) launch_dw<3, 2, 2>(a, st); else launch_dw<3, 2, 1>(a, st); }
+        else if (op.k == 5 && op.stride == 1) { if (wide) launch_dw<5, 1, 4>(a, st); else launch_dw<5, 1, 1>(a, st); }
+        else if (op.k == 5 && op.stride == 2) { if (wide) launch_dw<5, 2, 2>(a, st); else launch_dw<5, 2, 1>(a, st); }
+        else VBT_REQUIRE(false, "vbt_detect: depthwise kernel %dx%d stride %d", op.k, op.k, op.stride);
         break;
       }
       case OP_ADD:

@@ -19,6 +19,7 @@
 // HBM / epilogue bound, never tensor bound, so it favours many small co-resident CTAs
 // (several per SM overlap each other's loads, MMAs and epilogues) over a deep pipeline.
 #include "model.cuh"
+#include "requant.cuh"
 
 namespace {
 
@@ -33,10 +34,16 @@ struct PwUmmaArgs {
   long long M;
   int cin_p, cout_p, nc;        // nc: output columns per CTA (multiple of 16, <= 256)
   int zp_conv, lo, hi;
-  int has_res, res_zp, add_mult0, add_mult1, add_shift, zp_final;
+  int res_zp, add_mult0, add_mult1, add_shift, zp_final;
   int out_stride;               // staging row stride in bytes (odd multiple of 16)
   int tmem_cols;                // power of two >= max(32, nc)
+  uint32_t inv_kpad[2];         // ceil(65536 / kpad) of a full K stage and of the last one
+  uint32_t inv_cpr;             // ceil(65536 / (nc / 16)) per N chunk (last chunk: computed in-kernel)
+  vbt::Requant rq;              // conv requant; with a residual: to the full int8 range
 };
+
+// q / d for q < 4096, d <= 16, inv = ceil(65536 / d)
+__device__ __forceinline__ int div_small(int q, uint32_t inv) { return (int)(((uint32_t)q * inv) >> 16); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -83,6 +90,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+template <bool HAS_RES>
 __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -104,7 +112,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   const uint32_t ab = a_bytes + b_bytes;
   const uint32_t after = (ab > stage_bytes ? ab : stage_bytes);
   unsigned char* sRes = smem + ((after + 127) & ~127u);                 // residual tile (has_res)
-  int32_t* sBias = reinterpret_cast<int32_t*>(sRes + (a.has_res ? ((stage_bytes + 127) & ~127u) : 0));
+  int32_t* sBias = reinterpret_cast<int32_t*>(sRes + (HAS_RES ? ((stage_bytes + 127) & ~127u) : 0));
   float* sMult = reinterpret_cast<float*>(sBias + a.nc);
 
   if (warp == 0) {
@@ -117,10 +125,11 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   for (int i = tid; i < nc; i += 128) { sBias[i] = a.bias[n0 + i]; sMult[i] = a.mult[n0 + i]; }
-  if (a.has_res) {                                    // residual tile, row-padded like the output
+  if (HAS_RES) {                                    // residual tile, row-padded like the output
     const int cpr = nc >> 4;
+    const uint32_t inv_c = (nc == a.nc) ? a.inv_cpr : (65536u + cpr - 1) / cpr;
     for (int i = tid; i < TILE_M * cpr; i += 128) {
-      const int r = i / cpr, j = i - r * cpr;
+      const int r = div_small(i, inv_c), j = i - r * cpr;
       const long long m = m0 + r;
       const bool ok = m < a.M;
       cp_async16(smem_u32(sRes + (size_t)r * a.out_stride + j * 16),
@@ -140,13 +149,14 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   for (int kc0 = 0; kc0 < kch_total; kc0 += KCH_STAGE) {
     const int kch = min(KCH_STAGE, kch_total - kc0);
     const int kpad = (kch + 1) & ~1;
+    const uint32_t inv = a.inv_kpad[kch == kch_stage ? 0 : 1];
     // item = ((g * kch_pad + kc) * 8 + rr): shared address = item * 16 (linear), global =
     // row (g*8+rr), chunk kc.  Consecutive lanes walk rr fastest: 8 rows x 16 B = one
     // conflict-free 128-byte shared line; 4 chunks of the same row per warp coalesce.
     const int a_items = (TILE_M / 8) * kpad * 8;
     for (int it = tid; it < a_items; it += 128) {
       const int rr = it & 7, q = it >> 3;
-      const int g = q / kpad, kc = q - g * kpad;
+      const int g = div_small(q, inv), kc = q - g * kpad;
       const long long m = m0 + g * 8 + rr;
       const bool ok = (m < a.M) && (kc < kch);
       const uint32_t dst = smem_u32(sA) + (uint32_t)((g * kch_pad + kc) * 8 + rr) * 16;
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
     const int b_items = (nc / 8) * kpad * 8;
     for (int it = tid; it < b_items; it += 128) {
       const int rr = it & 7, q = it >> 3;
-      const int g = q / kpad, kc = q - g * kpad;
+      const int g = div_small(q, inv), kc = q - g * kpad;
       const int n = n0 + g * 8 + rr;
       const bool ok = kc < kch;
       const uint32_t dst = smem_u32(sB) + (uint32_t)((g * kch_pad + kc) * 8 + rr) * 16;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
         : "r"(trow + (uint32_t)c0));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
     uint4 rv = make_uint4(0, 0, 0, 0);
-    if (a.has_res) rv = *reinterpret_cast<const uint4*>(rrow + c0);
+    if (HAS_RES) rv = *reinterpret_cast<const uint4*>(rrow + c0);
     const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
     uint32_t packed[4];
 #pragma unroll
@@ -204,22 +214,17 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
       const float4 mq = *reinterpret_cast<const float4*>(sMult + c0 + q * 4);
       const int bs[4] = {bq.x, bq.y, bq.z, bq.w};
       const float ms[4] = {mq.x, mq.y, mq.z, mq.w};
-      uint32_t word = 0;
+      int y[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int acc = (int)v[q * 4 + j] + bs[j];
-        int y = __float2int_rn(__fmul_rn(__int2float_rn(acc), ms[j])) + a.zp_conv;
-        if (a.has_res) {
-          y = clampi(y, -128, 127);
+        y[j] = a.rq((int)v[q * 4 + j] + bs[j], ms[j]);
+        if (HAS_RES) {
           const int r = (int)(int8_t)(rw[q] >> (8 * j));
-          const int s = (y - a.zp_conv) * a.add_mult0 + (r - a.res_zp) * a.add_mult1 + round;
-          y = clampi((s >> a.add_shift) + a.zp_final, a.lo, a.hi);
-        } else {
-          y = clampi(y, a.lo, a.hi);
+          const int s = (y[j] - a.zp_conv) * a.add_mult0 + (r - a.res_zp) * a.add_mult1 + round;
+          y[j] = clampi((s >> a.add_shift) + a.zp_final, a.lo, a.hi);
         }
-        word |= (uint32_t)(y & 0xff) << (8 * j);
       }
-      packed[q] = word;
+      packed[q] = vbt::pack4_s8(y[0], y[1], y[2], y[3]);
     }
     *reinterpret_cast<uint4*>(orow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
@@ -228,8 +233,9 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   // ---- coalesced copy-out of the staged tile ----------------------------------------------
   {
     const int cpr = nc >> 4;
+    const uint32_t inv_c = (nc == a.nc) ? a.inv_cpr : (65536u + cpr - 1) / cpr;
     for (int i = tid; i < TILE_M * cpr; i += 128) {
-      const int r = i / cpr, j = i - r * cpr;
+      const int r = div_small(i, inv_c), j = i - r * cpr;
       const long long m = m0 + r;
       if (m < a.M)
         *reinterpret_cast<uint4*>(a.out + m * a.cout_p + n0 + j * 16) =
@@ -267,26 +273,40 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   a.cin_p = op.cin_p; a.cout_p = op.cout_p;
   const int n_chunks = (op.cout_p + 255) / 256;
   a.nc = ((op.cout_p + n_chunks - 1) / n_chunks + 15) / 16 * 16;
+  const bool has_res = res != nullptr;
   a.zp_conv = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
-  a.has_res = res != nullptr; a.res_zp = op.zp_in[1];
+  a.res_zp = op.zp_in[1];
   a.add_mult0 = op.add_mult[0]; a.add_mult1 = op.add_mult[1]; a.add_shift = op.add_shift;
   a.zp_final = op.zp_in[2];
+  // with a residual the conv result is an int8 intermediate: saturate, clamp after the add
+  a.rq = has_res ? Requant(op.zp_out, -128, 127) : Requant(op.zp_out, op.act_lo, op.act_hi);
   a.out_stride = ((a.nc / 16) | 1) * 16;
   int cols = 32;
   while (cols < a.nc) cols <<= 1;
   a.tmem_cols = cols;
-  const int kch = std::min(op.cin_p / 16, KCH_STAGE), kpad = (kch + 1) & ~1;
+  const int kch_total = op.cin_p / 16;
+  const int kch = std::min(kch_total, KCH_STAGE), kpad = (kch + 1) & ~1;
+  const int kch_last = kch_total - (kch_total - 1) / KCH_STAGE * KCH_STAGE, kpad_last = (kch_last + 1) & ~1;
+  a.inv_kpad[0] = (65536u + kpad - 1) / kpad;
+  a.inv_kpad[1] = (65536u + kpad_last - 1) / kpad_last;
+  a.inv_cpr = (65536u + a.nc / 16 - 1) / (a.nc / 16);
   const size_t ab = (size_t)(TILE_M + a.nc) * kpad * 16;
   const size_t stage = ((size_t)TILE_M * a.out_stride + 127) & ~(size_t)127;
-  size_t smem = ((std::max(ab, stage) + 127) & ~(size_t)127) + (a.has_res ? stage : 0) + (size_t)a.nc * 8 + 128;
+  size_t smem = ((std::max(ab, stage) + 127) & ~(size_t)127) + (has_res ? stage : 0) + (size_t)a.nc * 8 + 128;
+  // TMEM holds 512 columns per SM: ask for enough shared memory that no more CTAs become
+  // resident than can own `cols` columns each, so tcgen05.alloc never has to spin
+  const size_t cap_ctas = 512 / cols;
+  smem = std::max(smem, (size_t)228 * 1024 / (cap_ctas + 1));
   static bool attr_set = false;
   if (!attr_set) {
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (smem > 200 * 1024) return VBT_OK;
   dim3 grid((unsigned)((a.M + TILE_M - 1) / TILE_M), (unsigned)((op.cout_p + a.nc - 1) / a.nc));
-  pw_umma_kernel<<<grid, 128, smem, st>>>(a);
+  if (has_res) pw_umma_kernel<true><<<grid, 128, smem, st>>>(a);
+  else pw_umma_kernel<false><<<grid, 128, smem, st>>>(a);
   *taken = true;
   return VBT_OK;
 }

@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 2
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 3
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -572,13 +572,19 @@ def pack_blob(g: Graph):
                 wp[:cout, :ins[0].c] = q['w']
                 wsum = w.sum(axis=1)
             elif op.type == OP_DW:
-                # [k*k, c_p]: one 16-channel vector per tap
-                wp = np.zeros((op.k * op.k, cout_p), np.int8)
-                wp[:, :cout] = q['w'].reshape(cout, -1).T
+                # [k*k, c_p] 32-bit words, weight of channel c in byte (c % 4) and zeros
+                # elsewhere: dp4a(x_word, w_word) then multiplies exactly one channel of a
+                # 4-channel activation word, no unpacking in the kernel
+                wt = q['w'].reshape(cout, -1).T.astype(np.int64) & 0xff          # [k*k, cout]
+                wp = np.zeros((op.k * op.k, cout_p), np.uint32)
+                wp[:, :cout] = (wt << (8 * (np.arange(cout) % 4))[None, :]).astype(np.uint32)
                 wsum = w.reshape(cout, -1).sum(axis=1)
             else:
-                wp = np.zeros((cout_p, 28), np.int8)          # 27 taps (ky,kx,ci) + pad
-                wp[:cout, :27] = q['w'].reshape(cout, 27)
+                # stem: [9 pixel taps][cout_p] words = (w[.,0], w[.,1], w[.,2], 0): one dp4a
+                # per RGB pixel of the 3x3 window
+                w9 = q['w'].reshape(cout, 9, 3).astype(np.int64) & 0xff
+                wp = np.zeros((9, cout_p), np.uint32)
+                wp[:, :cout] = (w9[:, :, 0] | (w9[:, :, 1] << 8) | (w9[:, :, 2] << 16)).T.astype(np.uint32)
                 wsum = w.reshape(cout, -1).sum(axis=1)
             bias = np.zeros(cout_p, np.int32)
             bias[:cout] = (q['bias'].astype(np.int64) - zin * wsum).astype(np.int32)
