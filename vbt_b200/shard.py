@@ -1,0 +1,70 @@
+"""Multi-GPU sharding of the hot path: whole videos per rank, one gather at the end.
+
+The reference processes its sources one after the other, each with a fresh interpreter
+and a fresh tracker (track.py:88-101,157) and writes one pickle per video
+(track.py:117-126): videos are independent units, so the path shards with no data-path
+collective.  One process per GPU (`torch.distributed`, NCCL on the GPUs,
+gloo in the CPU tests):
+
+* ``lpt_assign``        -- greedy longest-processing-time deal of videos to ranks
+                           (frame count is the cost: every frame costs the same);
+* ``gather_row_tables`` -- the ONE exchange step: all_gather of per-video row counts,
+                           then all_gather of each rank's row tables packed into one
+                           padded [rows, 8] float64 buffer.  Never called per frame.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def lpt_assign(frame_counts, world_size):
+    """Video indices per rank.  Longest first, each to the currently lightest rank; ties go
+    to the lowest rank / lowest video index so every rank computes the same plan."""
+    order = sorted(range(len(frame_counts)), key=lambda i: (-int(frame_counts[i]), i))
+    load = [0] * world_size
+    plan = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        plan[r].append(i)
+        load[r] += int(frame_counts[i])
+    return plan
+
+
+def gather_row_tables(local_tables, n_videos, device=None, group=None):
+    """local_tables: {video index: float64 [n,8] row table} of THIS rank's videos.
+    Returns {video index: float64 [n,8]} holding every video, identical on every rank.
+
+    Two collectives in total: counts (int64 [n_videos]) and one padded payload."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return {k: np.asarray(v, dtype=np.float64).reshape(-1, 8) for k, v in local_tables.items()}
+    world = dist.get_world_size(group)
+    dev = device if device is not None else (
+        torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu'))
+    counts = torch.zeros(n_videos, dtype=torch.int64, device=dev)
+    for k, v in local_tables.items():
+        counts[k] = len(v)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    per_rank = [int(c.sum().item()) for c in all_counts]
+    pad = max(max(per_rank), 1)
+    payload = torch.zeros((pad, 8), dtype=torch.float64, device=dev)
+    at = 0
+    for k in sorted(local_tables):
+        t = torch.as_tensor(np.asarray(local_tables[k], dtype=np.float64).reshape(-1, 8), device=dev)
+        payload[at:at + len(t)] = t
+        at += len(t)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    out = {}
+    for r in range(world):
+        c = all_counts[r].cpu().numpy()
+        buf = gathered[r].cpu().numpy()
+        at = 0
+        for k in np.nonzero(c)[0]:
+            out[int(k)] = buf[at:at + int(c[k])].copy()
+            at += int(c[k])
+    for k in range(n_videos):
+        out.setdefault(k, np.zeros((0, 8)))
+    return out
