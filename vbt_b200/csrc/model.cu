@@ -107,6 +107,7 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
 void vbt_model_destroy(vbt_model* m) {
   if (!m) return;
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
+  for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
   if (m->dev_data) cudaFree(m->dev_data);
   delete m;
 }

@@ -1,6 +1,9 @@
 // Device-side description of one EfficientDet-Lite model: the layer program written by
 // vbt_b200/effdet.py, its weights, anchors and output quantisation.
 #pragma once
+#include <map>
+#include <set>
+#include <tuple>
 #include <vector>
 
 #include "common.cuh"
@@ -10,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 3;
+constexpr int kBlobVersion = 4;
 
 struct BlobHeader {
   uint32_t magic;
@@ -90,6 +93,15 @@ struct vbt_model {
   const float* dev_exp_lut = nullptr;
   int kernels_per_detect = 0;
   int device = -1;
+  // CUDA graphs of the layer program, one per (buffers, batch) a caller has used twice
+  struct GraphKey {
+    const void *in, *ws, *cls, *box; int B;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(in, ws, cls, box, B) < std::tie(o.in, o.ws, o.cls, o.box, o.B);
+    }
+  };
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::set<GraphKey> graph_seen;
   // optional per-op timing (bench.py): a ring of event sets, harvested lazily
   bool profile = false;
   static constexpr int kProfRing = 64;

@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
 // ---------------------------------------------------------------------------------------
 struct DwArgs {
   const int8_t* in; int8_t* out;
-  const uint32_t* w; const int32_t* bias; const float* mult;   // w [k*k][c_p] masked words
+  const uint32_t* w; const int32_t* bias; const float* mult;   // w [k*k][4][c_p/16][4] masked words
   int B, H, W, Ho, Wo, c_p, pad_top, pad_left, zp_in;
   vbt::Requant rq;
 };
@@ -173,10 +173,10 @@ __global__ void __launch_bounds__(128) dw_kernel(DwArgs a) {
       }
 #pragma unroll
       for (int kx = 0; kx < K; ++kx) {
-        const uint4* wp = reinterpret_cast<const uint4*>(a.w + (size_t)(ky * K + kx) * a.c_p + c0);
+        const uint4* wp = reinterpret_cast<const uint4*>(a.w) + (size_t)(ky * K + kx) * 4 * groups + gidx;
         uint4 wv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) wv[q] = __ldg(wp + q);
+        for (int q = 0; q < 4; ++q) wv[q] = __ldg(wp + (size_t)q * groups);
 #pragma unroll
         for (int p = 0; p < PX; ++p) {
           const uint4 xv = col[p * S + kx];
@@ -414,18 +414,13 @@ int grid_for(long long work_items, int threads) {
 
 }  // namespace
 
-extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace,
-                          size_t workspace_bytes, int8_t* dev_out_cls, int8_t* dev_out_box,
-                          void* stream) {
+namespace {
+
+// Enqueue the whole layer program on `st` (one launch per op).  `prof`: event set for the
+// per-op timing mode (bench.py), else nullptr.
+int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int8_t* dev_out_cls,
+            int8_t* dev_out_box, cudaStream_t st, cudaEvent_t* prof) {
   using namespace vbt;
-  VBT_REQUIRE(m && dev_in && dev_workspace && dev_out_cls && dev_out_box, "vbt_detect: null pointer");
-  VBT_REQUIRE(B > 0, "vbt_detect: B=%d", B);
-  VBT_REQUIRE(workspace_bytes >= (size_t)B * (size_t)m->hdr.ws_bytes_per_frame,
-              "vbt_detect: workspace of %zu bytes is smaller than B * %lld", workspace_bytes,
-              (long long)m->hdr.ws_bytes_per_frame);
-  VBT_REQUIRE(((uintptr_t)dev_workspace & 255) == 0, "vbt_detect: workspace must be 256-byte aligned");
-  VBT_REQUIRE(!m->ops.empty(), "vbt_detect: the model holds no layer program (anchors only)");
-  cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = static_cast<uint8_t*>(dev_workspace);
   const long long Np = m->hdr.n_anchors_pad;
   // tensors without a workspace slot (the model input) live in the caller's buffer
@@ -436,7 +431,6 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
   };
   auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
   int launched = 0;
-  cudaEvent_t* prof = profile_begin(m);
   if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], st));
   for (const OpRecord& op : m->ops) {
     switch (op.type) {
@@ -523,6 +517,57 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
     VBT_CHECK_CUDA(cudaPeekAtLastError());
     if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], st));
   }
-  vbt::count_launches(launched);
+  return VBT_OK;
+}
+
+}  // namespace
+
+extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace,
+                          size_t workspace_bytes, int8_t* dev_out_cls, int8_t* dev_out_box,
+                          void* stream) {
+  using namespace vbt;
+  VBT_REQUIRE(m && dev_in && dev_workspace && dev_out_cls && dev_out_box, "vbt_detect: null pointer");
+  VBT_REQUIRE(B > 0, "vbt_detect: B=%d", B);
+  VBT_REQUIRE(workspace_bytes >= (size_t)B * (size_t)m->hdr.ws_bytes_per_frame,
+              "vbt_detect: workspace of %zu bytes is smaller than B * %lld", workspace_bytes,
+              (long long)m->hdr.ws_bytes_per_frame);
+  VBT_REQUIRE(((uintptr_t)dev_workspace & 255) == 0, "vbt_detect: workspace must be 256-byte aligned");
+  VBT_REQUIRE(!m->ops.empty(), "vbt_detect: the model holds no layer program (anchors only)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_ops = (int)m->ops.size();
+  cudaEvent_t* prof = profile_begin(m);
+  // Replaying a captured CUDA graph turns the ~200 launches of a batch into one submission.
+  // Not on the legacy default stream (capture is illegal there), not while per-op timing is on.
+  static const bool use_graph = [] { const char* e = getenv("VBT_GRAPH"); return !(e && e[0] == '0'); }();
+  if (!use_graph || prof || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
+    if (int rc = run_ops(m, dev_in, B, dev_workspace, dev_out_cls, dev_out_box, st, prof)) return rc;
+    vbt::count_launches(n_ops);
+    return VBT_OK;
+  }
+  const vbt_model::GraphKey key{dev_in, dev_workspace, dev_out_cls, dev_out_box, B};
+  auto it = m->graphs.find(key);
+  if (it == m->graphs.end()) {
+    auto seen = m->graph_seen.find(key);
+    if (seen == m->graph_seen.end()) {
+      // first call with these buffers: run directly (also performs every one-time
+      // cudaFuncSetAttribute outside of a capture); capture on the next call
+      m->graph_seen.insert(key);
+      if (int rc = run_ops(m, dev_in, B, dev_workspace, dev_out_cls, dev_out_box, st, nullptr)) return rc;
+      vbt::count_launches(n_ops);
+      return VBT_OK;
+    }
+    cudaGraph_t graph = nullptr;
+    VBT_CHECK_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    const int rc = run_ops(m, dev_in, B, dev_workspace, dev_out_cls, dev_out_box, st, nullptr);
+    const cudaError_t e = cudaStreamEndCapture(st, &graph);
+    if (rc != VBT_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    VBT_CHECK_CUDA(e);
+    cudaGraphExec_t exec = nullptr;
+    VBT_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    it = m->graphs.emplace(key, exec).first;
+  }
+  VBT_CHECK_CUDA(cudaGraphLaunch(it->second, st));
+  vbt::count_launches(n_ops);
   return VBT_OK;
 }

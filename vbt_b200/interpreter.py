@@ -50,6 +50,7 @@ class Detector:
 
     def __init__(self, model, max_batch=64, iou_threshold=0.5, max_det=MAX_DET):
         self.torch = t = _lib.require_cuda()
+        self.source = model
         blob, self.name = load_model_bytes(model)
         h = C.c_void_p()
         _lib.check(_lib.lib().vbt_model_create(blob, len(blob), C.byref(h)))

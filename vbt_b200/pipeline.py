@@ -20,9 +20,20 @@ COLUMNS = ['id', 'time', 'x', 'y', 'dx', 'dy', 'norm_plate_height', 'norm_plate_
 
 
 class VideoPipeline:
+    """One video on one GPU.
+
+    Streams: `n_lanes` detection lanes (each its own stream, CUDA graph and detector
+    buffers) take the batches round robin, so two batches of the same video are in flight
+    and one lane's small late-network kernels overlap the other's large early ones;
+    tracking and velocity (K7, K8: a sequential recurrence over frames on one warp) follow
+    in batch order on the `side` stream, off the detector's critical path
+    (SURVEY.md 7.3-6).  Nothing returns to the host before `finish()`."""
+
+    N_SLOTS = 4          # ring of tracker-input slots between the lanes and the side stream
+
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
                  row_cap=1 << 17, id_lanes=32, tracker_kw=None, diff_threshold=0.6,
-                 min_distance=0.1):
+                 min_distance=0.1, n_lanes=2):
         self.torch = t = _lib.require_cuda()
         self.det = detector
         self.fps = float(fps)
@@ -33,21 +44,25 @@ class VideoPipeline:
         self.id_lanes = id_lanes
         self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
         D = detector.max_det
-        # Two slots of tracker inputs: the detector fills slot i while K7/K8 still read slot
-        # i^1 on the side stream (the recurrence over frames is latency-bound on one warp and
-        # must stay off the detector's critical path).
-        self.dets = t.zeros((2, 1, self.F, D, 6), dtype=t.float64, device='cuda')
-        self.det_count = t.zeros((2, 1, self.F), dtype=t.int32, device='cuda')
-        self.frame_no = t.zeros((2, 1, self.F), dtype=t.int32, device='cuda')
-        self.n_frames = t.zeros((2, 1), dtype=t.int32, device='cuda')
+        S = self.N_SLOTS
+        self.dets = t.zeros((S, 1, self.F, D, 6), dtype=t.float64, device='cuda')
+        self.det_count = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
+        self.frame_no = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
+        self.n_frames = t.zeros((S, 1), dtype=t.int32, device='cuda')
         self.d_fps = t.tensor([self.fps], dtype=t.float64, device='cuda')
         self.lane_table = t.zeros(id_lanes, dtype=t.int32, device='cuda')
         self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda')
         self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
+        self.detectors = [detector] + [Detector(detector.source, max_batch=detector.max_batch,
+                                                iou_threshold=detector.iou_threshold,
+                                                max_det=detector.max_det) for _ in range(n_lanes - 1)]
+        self.det_streams = [t.cuda.Stream() for _ in range(n_lanes)]
+        self.active_lanes = n_lanes                  # bench.py profiles with a single lane
         self.side = t.cuda.Stream()
-        self.det_ready = [t.cuda.Event() for _ in range(2)]
-        self.slot_free = [t.cuda.Event() for _ in range(2)]
-        self.slot = 0
+        self.det_ready = [t.cuda.Event() for _ in range(S)]
+        self.slot_free = [t.cuda.Event() for _ in range(S)]
+        self.input_consumed = None     # event: the last batch's frames have been read (K1 done)
+        self.batches = 0
         self.last_slot = 0
         self.frames_done = 0
         self.stage_events = None      # bench.py: list of per-step event tuples when profiling
@@ -58,9 +73,15 @@ class VideoPipeline:
             e.record(stream)
             marks.append(e)
 
+    def _sync_streams(self):
+        cur = self.torch.cuda.current_stream()
+        for s in self.det_streams:
+            cur.wait_stream(s)
+        cur.wait_stream(self.side)
+
     def reset(self, fps=None):
         t = self.torch
-        t.cuda.current_stream().wait_stream(self.side)
+        self._sync_streams()
         if fps is not None:
             self.fps = float(fps)
             self.d_fps.fill_(self.fps)
@@ -68,39 +89,49 @@ class VideoPipeline:
         self.lanes.reset()
         self.lane_begin.zero_()
         self.frames_done = 0
-        self.side.wait_stream(t.cuda.current_stream())
+        cur = t.cuda.current_stream()
+        for s in self.det_streams:
+            s.wait_stream(cur)
+        self.side.wait_stream(cur)
 
     def process(self, frames, frame_numbers, swap_rb=True):
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
-        tensor [n] with the 1-based frame_count of each (track.py:161).
-        Detection (K1, network, K6, packing) is enqueued on the current stream; tracking and
-        velocity (K7, K8) follow on `self.side`, overlapping the next batch's detection."""
+        tensor [n] with the 1-based frame_count of each (track.py:161).  Both must be ready on
+        the current stream; `self.input_consumed` is recorded once K1 has read `frames`."""
         t = self.torch
-        main = t.cuda.current_stream()
         n = frames.shape[0]
-        marks = [] if self.stage_events is not None else None
-        self._mark(marks)
-        det = self.det
-        images = det.preprocess(frames, swap_rb)
-        self._mark(marks)
-        det.network(images)
-        self._mark(marks)
-        boxes, _, scores, count, _ = det.postprocess(n, score_to_q(self.threshold))
-        self._mark(marks)
-        k = self.slot
-        self.slot ^= 1
+        lane = self.batches % self.active_lanes
+        k = self.batches % self.N_SLOTS
+        self.batches += 1
         self.last_slot = k
-        main.wait_event(self.slot_free[k])           # K7 of two batches ago has read slot k
-        _lib.check(_lib.lib().vbt_pack_detections(
-            boxes.data_ptr(), scores.data_ptr(), count.data_ptr(), n, self.det.max_det,
-            self.threshold, self.dets[k].data_ptr(), self.det_count[k].data_ptr(),
-            _lib.stream_ptr(main)))
-        self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
-        self.n_frames[k].fill_(n)
-        self._mark(marks)
-        self.det_ready[k].record(main)
+        det, ds = self.detectors[lane], self.det_streams[lane]
+        marks = [] if self.stage_events is not None else None
+        arrived = t.cuda.Event()
+        arrived.record()
+        ds.wait_event(arrived)
+        frames.record_stream(ds)
+        frame_numbers.record_stream(ds)
+        with t.cuda.stream(ds):
+            self._mark(marks)
+            images = det.preprocess(frames, swap_rb)
+            self.input_consumed = t.cuda.Event()
+            self.input_consumed.record(ds)
+            self._mark(marks)
+            det.network(images)
+            self._mark(marks)
+            boxes, _, scores, count, _ = det.postprocess(n, score_to_q(self.threshold))
+            self._mark(marks)
+            ds.wait_event(self.slot_free[k])           # K7 has read this slot's previous batch
+            _lib.check(_lib.lib().vbt_pack_detections(
+                boxes.data_ptr(), scores.data_ptr(), count.data_ptr(), n, det.max_det,
+                self.threshold, self.dets[k].data_ptr(), self.det_count[k].data_ptr(),
+                _lib.stream_ptr(ds)))
+            self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
+            self.n_frames[k].fill_(n)
+            self._mark(marks)
+            self.det_ready[k].record(ds)
         side = self.side
-        side.wait_event(self.det_ready[k])
+        side.wait_event(self.det_ready[k])             # batches reach the side stream in order
         with t.cuda.stream(side):
             self._mark(marks, side)
             self.tracker.update(self.dets[k], self.det_count[k], self.frame_no[k], self.d_fps,
@@ -119,7 +150,7 @@ class VideoPipeline:
     def finish(self):
         """End of video: run end_processing() on every lane, bring results to the host.
         Returns dict(rows=f64[n,8] append order, phases={id: [Phase]}, path={id: float})."""
-        self.torch.cuda.current_stream().wait_stream(self.side)
+        self._sync_streams()
         self.tracker.check_status()
         self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
                           self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,

@@ -43,20 +43,27 @@ def track(src, interpreter, detection_treshold, display_image_height=720, video_
     pipe = VideoPipeline(det, fps, detection_treshold,
                          tracker_kw=dict(max_age=MAX_AGE, iou_threshold=0.1))   # track.py:157
     staged, numbers = [], []
-    pinned = None
+    pinned, copied = [None, None], [None, None]     # two pinned staging buffers, ping-pong
+    flushes = 0
     frame_count = 0
 
     def flush():
-        nonlocal pinned
+        nonlocal flushes
         if not staged:
             return
         n = len(staged)
         h, w = staged[0].shape[:2]
-        if pinned is None or pinned.shape[1:3] != (h, w):
-            pinned = torch.empty((batch, h, w, 3), dtype=torch.uint8).pin_memory()
+        k = flushes & 1
+        flushes += 1
+        if pinned[k] is None or pinned[k].shape[1:3] != (h, w):
+            pinned[k] = torch.empty((batch, h, w, 3), dtype=torch.uint8).pin_memory()
+        if copied[k] is not None:
+            copied[k].synchronize()                 # the H2D copy that last read this buffer is done
         for i, f in enumerate(staged):
-            pinned[i].copy_(torch.from_numpy(f))
-        dev = pinned[:n].to('cuda', non_blocking=True)
+            pinned[k][i].copy_(torch.from_numpy(f))
+        dev = pinned[k][:n].to('cuda', non_blocking=True)
+        copied[k] = torch.cuda.Event()
+        copied[k].record()
         nums = torch.as_tensor(np.asarray(numbers, dtype=np.int32), device='cuda')
         pipe.process(dev, nums, swap_rb=True)          # cv2 frames are BGR (track.py:171)
         staged.clear()
