@@ -41,6 +41,20 @@ def test_preprocess_bit_exact(shape, S, swap):
     assert np.array_equal(out.cpu().numpy(), want)
 
 
+def test_preprocess_reads_pinned_host_frames_in_place():
+    """Zero-copy ingest: K1 pulls the source rows it needs straight from pinned host memory."""
+    import torch
+    from vbt_b200 import _lib
+    rng = np.random.default_rng(11)
+    frames = rng.integers(0, 256, size=(2, 1080, 1920, 3), dtype=np.uint8)
+    host = torch.from_numpy(frames).pin_memory()
+    out = torch.empty((2, 320, 320, 3), dtype=torch.uint8, device='cuda')
+    _lib.check(_lib.lib().vbt_preprocess_u8(host.data_ptr(), 2, 1080, 1920, 1, out.data_ptr(), 320,
+                                            _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), OR.preprocess_batch(frames, 320, swap_rb=True))
+
+
 def test_preprocess_image_helper_matches_oracle():
     from vbt_b200.odt import preprocess_image
     rng = np.random.default_rng(1)

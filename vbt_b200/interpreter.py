@@ -92,7 +92,11 @@ class Detector:
 
     # -- stages ----------------------------------------------------------------------------
     def preprocess(self, frames, swap_rb=True, stream=None):
-        """frames: uint8 CUDA tensor [B,H,W,3] -> self.resized[:B] (RGB, SxS)."""
+        """frames: uint8 [B,H,W,3], a CUDA tensor or a PINNED host tensor (read in place over
+        PCIe: only the 2*S source rows the bilinear kernel touches cross the bus)
+        -> self.resized[:B] (RGB, SxS)."""
+        if not frames.is_cuda and not frames.is_pinned():
+            raise ValueError('host frames must be in pinned memory (tensor.pin_memory())')
         B, H, W, _ = frames.shape
         assert B <= self.max_batch and frames.is_contiguous()
         _lib.check(_lib.lib().vbt_preprocess_u8(frames.data_ptr(), B, H, W, int(swap_rb),

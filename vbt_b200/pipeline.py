@@ -9,6 +9,8 @@ phases to the host, where the DataFrame of track.py:103-126 is assembled with pa
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from . import _lib
@@ -33,8 +35,10 @@ class VideoPipeline:
 
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
                  row_cap=1 << 17, id_lanes=32, tracker_kw=None, diff_threshold=0.6,
-                 min_distance=0.1, n_lanes=2):
+                 min_distance=0.1, n_lanes=None):
         self.torch = t = _lib.require_cuda()
+        if n_lanes is None:
+            n_lanes = max(1, int(os.environ.get('VBT_LANES', '2')))
         self.det = detector
         self.fps = float(fps)
         self.threshold = float(detection_threshold)
@@ -109,7 +113,8 @@ class VideoPipeline:
         arrived = t.cuda.Event()
         arrived.record()
         ds.wait_event(arrived)
-        frames.record_stream(ds)
+        if frames.is_cuda:              # pinned host frames are read in place by K1 (zero copy)
+            frames.record_stream(ds)
         frame_numbers.record_stream(ds)
         with t.cuda.stream(ds):
             self._mark(marks)
