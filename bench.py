@@ -139,6 +139,7 @@ def run_reference(args, rank):
     from oracle.cpu_pipeline import CpuPipeline
     from vbt_b200 import effdet
     from vbt_b200.synth import plate_trajectory
+    torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
     g = effdet.build_synthetic(args.variant)
     per_step = max(1, min(4, 60 // max(args.steps, 1)))
     rng = np.random.default_rng(0)
@@ -168,7 +169,7 @@ def run_reference(args, rank):
     cores = torch.get_num_threads()
     sample = (f'{args.steps} steps x {per_step} frame(s) of the same synthetic 1080p clip, batch 1 per '
               f'frame like track.py; int8-exact oracle (fp64 conv on torch CPU), all host threads')
-    print(json.dumps({
+    emit(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'frames/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8',
@@ -181,8 +182,21 @@ def run_reference(args, rank):
     }))
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print meanwhile (NCCL's
+    version banner, warnings) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (line + '\n').encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -446,7 +460,7 @@ def main():
             'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu,
             'clocks': clocks, 'kernels': breakdown,
         }
-        print(json.dumps(out))
+        emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
