@@ -40,4 +40,25 @@ int ensure_device();  // VBT_OK when an sm_100 device is current, else VBT_ECUDA
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch: consecutive kernels of the layer program are launched with
+// the stream-serialisation attribute, so the next kernel's CTAs are scheduled while the
+// previous kernel drains and run their prologue (weight loads, TMEM allocation, barrier
+// init).  Every such kernel calls pdl_wait() before it touches anything a predecessor wrote
+// (or that a predecessor may still be reading), then pdl_launch_dependents().
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename Arg>
+cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, arg);
+}
+#endif
+
 }  // namespace vbt

@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 4;
+constexpr int kBlobVersion = 5;
 
 struct BlobHeader {
   uint32_t magic;

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
   for (int i = threadIdx.x; i < a.cout_p * 9; i += blockDim.x) sw[i] = a.w[i];
   for (int i = threadIdx.x; i < a.cout_p; i += blockDim.x) { sb[i] = a.bias[i]; sm[i] = a.mult[i]; }
   __syncthreads();
+  vbt::pdl_wait();
+  vbt::pdl_launch_dependents();
   const long long total = (long long)a.B * a.Ho * a.Wo;
   const uint32_t zpix = (uint32_t)a.zp_in * 0x010101u;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total;
@@ -117,110 +119,157 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------
-// depthwise KxK (K = 3 or 5, stride 1 or 2, TF-SAME).  One thread = PX consecutive output
-// pixels of one row x 16 channels.  Weights are pre-masked 32-bit words (channel c in byte
-// c % 4, see effdet.pack_blob), so a tap is 16 dp4a on the four activation words of the
-// pixel with no byte unpacking; the (PX-1)*S+K input columns of a row are loaded once
-// (128-bit) and shared by the PX outputs.  Channel groups vary fastest across threads, so
-// a warp reads whole 128-byte lines.
+// depthwise KxK (K = 3 or 5, stride 1 or 2, TF-SAME), channel-word stationary.
+//
+// One thread owns ONE 32-bit activation word (4 channels) and keeps everything that
+// depends only on the channel in registers for its whole life: the K*K*4 pre-masked weight
+// words (channel j of the word in byte j, see effdet.pack_blob -- dp4a(x_word, w_word)
+// multiplies exactly one channel, no unpacking), 4 biases, 4 multipliers.  It then walks
+// row segments of L output pixels in groups of J: the (J-1)*S+K window columns of a group
+// are loaded together (32-bit loads), then each output is K*K*4 dp4a.  Consecutive
+// threads hold consecutive channel words, so every load / store of a warp is one contiguous
+// 128-byte line (or whole 32-byte sectors when the tensor has fewer than 128 channels):
+// the L1 wavefront count per output drops ~10x against a 16-channel-per-thread layout.
 // ---------------------------------------------------------------------------------------
 struct DwArgs {
   const int8_t* in; int8_t* out;
-  const uint32_t* w; const int32_t* bias; const float* mult;   // w [k*k][4][c_p/16][4] masked words
+  const uint32_t* w; const int32_t* bias; const float* mult;   // w [k*k][c_p] masked words
   int B, H, W, Ho, Wo, c_p, pad_top, pad_left, zp_in;
+  int words, wx, seg_len, n_seg;       // c_p/4, word lanes per CTA, outputs per segment, segments per row
+  long long n_items;                   // B * Ho * n_seg
   vbt::Requant rq;
 };
 
-template <int K, int S, int PX>
-__global__ void __launch_bounds__(128) dw_kernel(DwArgs a) {
-  constexpr int NCOL = (PX - 1) * S + K;
-  const int groups = a.c_p >> 4;
-  const int xb_n = (a.Wo + PX - 1) / PX;
-  const long long total = (long long)a.B * a.Ho * xb_n * groups;
-  const uint32_t zpw = (uint32_t)(a.zp_in & 0xff) * 0x01010101u;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int gidx = (int)(i % groups);
-    long long r = i / groups;
-    const int xb = (int)(r % xb_n); r /= xb_n;
-    const int oy = (int)(r % a.Ho), b = (int)(r / a.Ho);
-    const int c0 = gidx << 4, ox0 = xb * PX;
-    int acc[PX][16];
-    {
-      const int4* bp = reinterpret_cast<const int4*>(a.bias + c0);
+template <int K, int S>
+__global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
+  constexpr int J = (K == 5) ? (S == 1 ? 4 : 2) : (S == 1 ? 4 : 2);     // outputs per group
+  constexpr bool kSmemW = (K == 5);   // 5x5: the 100 weight words live in shared memory, not registers
+  constexpr int NCOL = (J - 1) * S + K;
+  const int wl = threadIdx.x % a.wx, il = threadIdx.x / a.wx;
+  const int il_n = blockDim.x / a.wx;
+  const int cw = blockIdx.y * a.wx + wl;
+  if (cw >= a.words || il >= il_n) return;
+  // channel-stationary state
+  extern __shared__ __align__(16) uint4 sw[];         // [K*K][blockDim.x] when kSmemW
+  uint32_t w[kSmemW ? 1 : K * K][4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const int4 v = __ldg(bp + q);
-#pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          acc[p][q * 4 + 0] = v.x; acc[p][q * 4 + 1] = v.y; acc[p][q * 4 + 2] = v.z; acc[p][q * 4 + 3] = v.w;
-        }
-      }
+  for (int t = 0; t < K * K; ++t) {
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(a.w + (size_t)t * a.c_p) + cw);
+    if (kSmemW) {
+      sw[t * blockDim.x + threadIdx.x] = v;           // read back only by this thread: no barrier
+    } else {
+      w[t][0] = v.x; w[t][1] = v.y; w[t][2] = v.z; w[t][3] = v.w;
     }
-    const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.c_p + c0;
-    const int ix0 = ox0 * S - a.pad_left;
+  }
+  const int4 bias = __ldg(reinterpret_cast<const int4*>(a.bias) + cw);
+  const float4 mult = __ldg(reinterpret_cast<const float4*>(a.mult) + cw);
+  const uint32_t zpw = (uint32_t)(a.zp_in & 0xff) * 0x01010101u;
+  const uint32_t* in = reinterpret_cast<const uint32_t*>(a.in) + cw;
+  uint32_t* out = reinterpret_cast<uint32_t*>(a.out) + cw;
+  const size_t words = (size_t)a.words;
+  vbt::pdl_wait();
+  vbt::pdl_launch_dependents();
+
+  for (long long item = (long long)blockIdx.x * il_n + il; item < a.n_items;
+       item += (long long)gridDim.x * il_n) {
+    const int seg = (int)(item % a.n_seg);
+    long long r = item / a.n_seg;
+    const int oy = (int)(r % a.Ho), b = (int)(r / a.Ho);
+    const int x0 = seg * a.seg_len, x1 = min(x0 + a.seg_len, a.Wo);
+    const uint32_t* fin = in + (size_t)b * a.H * a.W * words;
+    const uint32_t* rowp[K];
+    bool row_ok[K];
+    bool rows_in = true;
 #pragma unroll
     for (int ky = 0; ky < K; ++ky) {
       const int iy = oy * S - a.pad_top + ky;
-      const bool row_ok = iy >= 0 && iy < a.H;
-      uint4 col[NCOL];
+      row_ok[ky] = iy >= 0 && iy < a.H;
+      rows_in = rows_in && row_ok[ky];
+      rowp[ky] = fin + (size_t)(row_ok[ky] ? iy : 0) * a.W * words;
+    }
+    // J outputs per group: all (J-1)*S+K window columns are loaded first (independent loads in
+    // flight together), then the J outputs are computed from registers
+    uint32_t* orow = out + (((size_t)b * a.Ho + oy) * a.Wo) * words;
+    for (int xg = x0; xg < x1; xg += J) {
+      uint32_t win[NCOL][K];
+      const int ixb = xg * S - a.pad_left;
+      if (rows_in && ixb >= 0 && ixb + NCOL <= a.W) {       // interior: no predicates
+        int idx = ixb * a.words;
 #pragma unroll
-      for (int j = 0; j < NCOL; ++j) {
-        const int ix = ix0 + j;
-        col[j] = make_uint4(zpw, zpw, zpw, zpw);
-        if (row_ok && ix >= 0 && ix < a.W)
-          col[j] = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.c_p));
-      }
+        for (int c = 0; c < NCOL; ++c) {
 #pragma unroll
-      for (int kx = 0; kx < K; ++kx) {
-        const uint4* wp = reinterpret_cast<const uint4*>(a.w) + (size_t)(ky * K + kx) * 4 * groups + gidx;
-        uint4 wv[4];
+          for (int ky = 0; ky < K; ++ky) win[c][ky] = __ldg(rowp[ky] + idx);
+          idx += a.words;
+        }
+      } else {                                              // image border: zero-point padding
 #pragma unroll
-        for (int q = 0; q < 4; ++q) wv[q] = __ldg(wp + (size_t)q * groups);
+        for (int c = 0; c < NCOL; ++c) {
+          const int ix = ixb + c;
+          const bool col_ok = ix >= 0 && ix < a.W;
+          const int idx = (col_ok ? ix : 0) * a.words;
 #pragma unroll
-        for (int p = 0; p < PX; ++p) {
-          const uint4 xv = col[p * S + kx];
-          const uint32_t xs[4] = {xv.x, xv.y, xv.z, xv.w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[p][q * 4 + 0] = __dp4a((int)xs[q], (int)wv[q].x, acc[p][q * 4 + 0]);
-            acc[p][q * 4 + 1] = __dp4a((int)xs[q], (int)wv[q].y, acc[p][q * 4 + 1]);
-            acc[p][q * 4 + 2] = __dp4a((int)xs[q], (int)wv[q].z, acc[p][q * 4 + 2]);
-            acc[p][q * 4 + 3] = __dp4a((int)xs[q], (int)wv[q].w, acc[p][q * 4 + 3]);
+          for (int ky = 0; ky < K; ++ky) {
+            const uint32_t v = __ldg(rowp[ky] + idx);
+            win[c][ky] = (col_ok && row_ok[ky]) ? v : zpw;
           }
         }
       }
-    }
-    float ms[16];
-    {
-      const float4* mp = reinterpret_cast<const float4*>(a.mult + c0);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 mv = __ldg(mp + q);
-        ms[q * 4 + 0] = mv.x; ms[q * 4 + 1] = mv.y; ms[q * 4 + 2] = mv.z; ms[q * 4 + 3] = mv.w;
-      }
-    }
-    int8_t* orow = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox0) * a.c_p + c0;
+      for (int j = 0; j < J; ++j) {
+        const int x = xg + j;
+        if (x < x1) {
+          int acc0 = bias.x, acc1 = bias.y, acc2 = bias.z, acc3 = bias.w;
 #pragma unroll
-    for (int p = 0; p < PX; ++p) {
-      if (ox0 + p < a.Wo) {
-        uint32_t packed[4];
+          for (int ky = 0; ky < K; ++ky) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          packed[q] = vbt::pack4_s8(a.rq(acc[p][q * 4 + 0], ms[q * 4 + 0]), a.rq(acc[p][q * 4 + 1], ms[q * 4 + 1]),
-                                    a.rq(acc[p][q * 4 + 2], ms[q * 4 + 2]), a.rq(acc[p][q * 4 + 3], ms[q * 4 + 3]));
-        *reinterpret_cast<uint4*>(orow + (size_t)p * a.c_p) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+            for (int kx = 0; kx < K; ++kx) {
+              const int xv = (int)win[j * S + kx][ky];
+              const int t = ky * K + kx;
+              uint4 wv;
+              if (kSmemW) wv = sw[t * blockDim.x + threadIdx.x];
+              else wv = make_uint4(w[t][0], w[t][1], w[t][2], w[t][3]);
+              acc0 = __dp4a(xv, (int)wv.x, acc0);
+              acc1 = __dp4a(xv, (int)wv.y, acc1);
+              acc2 = __dp4a(xv, (int)wv.z, acc2);
+              acc3 = __dp4a(xv, (int)wv.w, acc3);
+            }
+          }
+          orow[(size_t)x * words] = vbt::pack4_s8(a.rq(acc0, mult.x), a.rq(acc1, mult.y),
+                                                  a.rq(acc2, mult.z), a.rq(acc3, mult.w));
+        }
       }
     }
   }
 }
 
-template <int K, int S, int PX>
-void launch_dw(const DwArgs& a, cudaStream_t st) {
-  const long long items = (long long)a.B * a.Ho * ((a.Wo + PX - 1) / PX) * (a.c_p / 16);
-  long long g = (items + 127) / 128;
-  const long long cap = 148LL * 32;
-  dw_kernel<K, S, PX><<<(int)(g < 1 ? 1 : (g > cap ? cap : g)), 128, 0, st>>>(a);
+template <int K, int S>
+int launch_dw(DwArgs a, cudaStream_t st) {
+  constexpr int kMaxThreads = (K == 5) ? 128 : 256;   // 5x5: ~145 registers per thread
+  a.words = a.c_p / 4;
+  const int chunks = (a.words + kMaxThreads - 1) / kMaxThreads;
+  a.wx = (a.words + chunks - 1) / chunks;
+  int il_n = kMaxThreads / a.wx;
+  if (il_n < 1) il_n = 1;
+  const int threads = a.wx * il_n;
+  // segment length: long enough to amortise the K-S warm-up columns, short enough to give
+  // every SM several CTAs of work
+  a.seg_len = a.Wo <= 24 ? a.Wo : 16;
+  a.n_seg = (a.Wo + a.seg_len - 1) / a.seg_len;
+  a.n_items = (long long)a.B * a.Ho * a.n_seg;
+  long long gx = (a.n_items + il_n - 1) / il_n;
+  const long long cap = 148LL * 8;
+  if (gx > cap) gx = cap;
+  dim3 grid((unsigned)gx, (unsigned)chunks);
+  const size_t smem = (K == 5) ? (size_t)K * K * threads * sizeof(uint4) : 0;
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      attr_set = true;
+    }
+  }
+  VBT_CHECK_CUDA(vbt::launch_pdl(dw_kernel<K, S>, grid, dim3(threads), smem, st, a));
+  return VBT_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -264,6 +313,8 @@ __device__ __forceinline__ uint4 fetch_resampled(const int8_t* base, int b, int 
 }
 
 __global__ void __launch_bounds__(256) add_kernel(AddArgs a) {
+  vbt::pdl_wait();
+  vbt::pdl_launch_dependents();
   const int groups = a.c_p >> 4;
   const long long total = (long long)a.B * a.Ho * a.Wo * groups;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -328,6 +379,8 @@ __global__ void __launch_bounds__(256) pw_dp4a_kernel(PwArgs a) {
   const long long m0 = (long long)blockIdx.x * PW_BM;
   const int n0 = blockIdx.y * PW_BN;
   const int ty = tid >> 4, tx = tid & 15;     // rows ty*4..+3 ; cols tx + 16*j
+  vbt::pdl_wait();
+  vbt::pdl_launch_dependents();
   int acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -444,7 +497,7 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         a.cout_p = op.cout_p; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
         a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
         VBT_REQUIRE(op.cout_p <= 64 && op.k == 3 && op.stride == 2, "vbt_detect: unsupported stem");
-        stem_kernel<<<grid_for((long long)B * op.h_out * op.w_out, 128), 128, 0, st>>>(a);
+        VBT_CHECK_CUDA(launch_pdl(stem_kernel, dim3(grid_for((long long)B * op.h_out * op.w_out, 128)), dim3(128), 0, st, a));
         break;
       }
       case OP_DW: {
@@ -456,12 +509,13 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out; a.c_p = op.cout_p;
         a.pad_top = op.pad_top; a.pad_left = op.pad_left;
         a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
-        const bool wide = op.w_out >= 8;          // tiny levels: one pixel per thread
-        if (op.k == 3 && op.stride == 1) { if (wide) launch_dw<3, 1, 4>(a, st); else launch_dw<3, 1, 1>(a, st); }
-        else if (op.k == 3 && op.stride == 2) { if (wide) launch_dw<3, 2, 2>(a, st); else launch_dw<3, 2, 1>(a, st); }
-        else if (op.k == 5 && op.stride == 1) { if (wide) launch_dw<5, 1, 4>(a, st); else launch_dw<5, 1, 1>(a, st); }
-        else if (op.k == 5 && op.stride == 2) { if (wide) launch_dw<5, 2, 2>(a, st); else launch_dw<5, 2, 1>(a, st); }
+        int rc = VBT_OK;
+        if (op.k == 3 && op.stride == 1) rc = launch_dw<3, 1>(a, st);
+        else if (op.k == 3 && op.stride == 2) rc = launch_dw<3, 2>(a, st);
+        else if (op.k == 5 && op.stride == 1) rc = launch_dw<5, 1>(a, st);
+        else if (op.k == 5 && op.stride == 2) rc = launch_dw<5, 2>(a, st);
         else VBT_REQUIRE(false, "vbt_detect: depthwise kernel %dx%d stride %d", op.k, op.k, op.stride);
+        if (rc) return rc;
         break;
       }
       case OP_ADD:
@@ -476,7 +530,7 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         a.shift = op.add_shift; a.zp_out = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
         a.pool_only = (op.type == OP_MAXPOOL);
         a.out = tensor_ptr(op.out);
-        add_kernel<<<grid_for((long long)B * op.h_out * op.w_out * (op.cout_p / 16), 256), 256, 0, st>>>(a);
+        VBT_CHECK_CUDA(launch_pdl(add_kernel, dim3(grid_for((long long)B * op.h_out * op.w_out * (op.cout_p / 16), 256)), dim3(256), 0, st, a));
         break;
       }
       case OP_PW: {
@@ -506,7 +560,7 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
           a.out_elem_offset = op.out_elem_offset;
           a.vector_out = (op.out_kind == 0);
           dim3 grid((unsigned)((a.M + PW_BM - 1) / PW_BM), (unsigned)((op.cout_p + PW_BN - 1) / PW_BN));
-          pw_dp4a_kernel<<<grid, 256, 0, st>>>(a);
+          VBT_CHECK_CUDA(launch_pdl(pw_dp4a_kernel, grid, dim3(256), 0, st, a));
         }
         break;
       }

@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   for (int i = tid; i < nc; i += 128) { sBias[i] = a.bias[n0 + i]; sMult[i] = a.mult[n0 + i]; }
+  vbt::pdl_wait();                 // everything above touched only model constants and this CTA's own state
+  vbt::pdl_launch_dependents();
   if (HAS_RES) {                                    // residual tile, row-padded like the output
     const int cpr = nc >> 4;
     const uint32_t inv_c = (nc == a.nc) ? a.inv_cpr : (65536u + cpr - 1) / cpr;
@@ -310,8 +312,8 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   }
   if (smem > 200 * 1024) return VBT_OK;
   dim3 grid((unsigned)((a.M + TILE_M - 1) / TILE_M), (unsigned)((op.cout_p + a.nc - 1) / a.nc));
-  if (has_res) pw_umma_kernel<true><<<grid, 128, smem, st>>>(a);
-  else pw_umma_kernel<false><<<grid, 128, smem, st>>>(a);
+  if (has_res) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<true>, grid, dim3(128), smem, st, a));
+  else VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false>, grid, dim3(128), smem, st, a));
   *taken = true;
   return VBT_OK;
 }

@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 4
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 5
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -578,9 +578,6 @@ def pack_blob(g: Graph):
                 wt = q['w'].reshape(cout, -1).T.astype(np.int64) & 0xff          # [k*k, cout]
                 wp = np.zeros((op.k * op.k, cout_p), np.uint32)
                 wp[:, :cout] = (wt << (8 * (np.arange(cout) % 4))[None, :]).astype(np.uint32)
-                # stored [tap][q][group][4]: channel 16*group + 4*q + j, so that the threads of
-                # a warp (consecutive channel groups) read consecutive 16-byte pieces
-                wp = np.ascontiguousarray(wp.reshape(op.k * op.k, cout_p // 16, 4, 4).transpose(0, 2, 1, 3))
                 wsum = w.reshape(cout, -1).sum(axis=1)
             else:
                 # stem: [9 pixel taps][cout_p] words = (w[.,0], w[.,1], w[.,2], 0): one dp4a
