@@ -1,8 +1,8 @@
-# usage: bash scripts/gpu_sweep.sh <tag> <ENVVAR> "<v1> <v2> ..."   (under gpurun): short bench per value
-TAG=$1; VAR=$2
+# usage: bash scripts/gpu_sweep.sh <tag> <ENVVAR> "<v1> <v2> ..." [extra bench args]  (under gpurun)
+TAG=$1; VAR=$2; EXTRA=${4:-"--steps 40 --warmup 4 --no-e2e --no-cpu-baseline"}
 mkdir -p gpurun_out
 for V in $3; do
-  env $VAR=$V timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --clip-frames 256 \
+  env $VAR=$V timeout 300 python bench.py $EXTRA \
      --op-dump gpurun_out/${TAG}_${VAR}_${V}_ops.tsv > gpurun_out/${TAG}_${VAR}_${V}.json 2> gpurun_out/${TAG}_${VAR}_${V}.err
   python - <<PY
 import json

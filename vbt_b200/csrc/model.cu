@@ -100,6 +100,31 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
   m->dev_anchors = reinterpret_cast<const float*>(m->dev_data + hdr.anchors_off);
   m->dev_exp_lut = reinterpret_cast<const float*>(m->dev_data + hdr.exp_lut_off);
   m->kernels_per_detect = hdr.n_ops;
+  for (const OpRecord& op : m->ops) {
+    if (op.branch < 0 || op.branch > vbt_model::kMaxBranches) {
+      vbt_model_destroy(m);
+      set_error("vbt_model_create: op branch %d outside 0..%d", op.branch, vbt_model::kMaxBranches);
+      return VBT_EFORMAT;
+    }
+    if (op.branch > m->n_branches) m->n_branches = op.branch;
+  }
+  for (int k = 0; k < m->n_branches; ++k) {
+    VBT_CHECK_CUDA(cudaStreamCreateWithFlags(&m->branch_stream[k], cudaStreamNonBlocking));
+    VBT_CHECK_CUDA(cudaEventCreateWithFlags(&m->join_event[k], cudaEventDisableTiming));
+  }
+  // a branch may start as soon as the trunk op that writes its input tensor is enqueued
+  for (int k = 0; k < m->n_branches; ++k) {
+    VBT_CHECK_CUDA(cudaEventCreateWithFlags(&m->fork_event[k], cudaEventDisableTiming));
+    int first = -1, last_trunk = -1;
+    for (int i = 0; i < (int)m->ops.size(); ++i) {
+      if (m->ops[i].branch == 0) last_trunk = i;
+      if (m->ops[i].branch == k + 1 && first < 0) first = i;
+    }
+    m->fork_after[k] = last_trunk;
+    if (first >= 0)
+      for (int i = 0; i < (int)m->ops.size(); ++i)
+        if (m->ops[i].branch == 0 && m->ops[i].out == m->ops[first].in[0]) m->fork_after[k] = i;
+  }
   *out = m;
   return VBT_OK;
 }
@@ -108,6 +133,12 @@ void vbt_model_destroy(vbt_model* m) {
   if (!m) return;
   for (cudaEvent_t e : m->prof_events) cudaEventDestroy(e);
   for (auto& kv : m->graphs) cudaGraphExecDestroy(kv.second);
+  for (int k = 0; k < vbt_model::kMaxBranches; ++k) {
+    if (m->branch_stream[k]) cudaStreamDestroy(m->branch_stream[k]);
+    if (m->join_event[k]) cudaEventDestroy(m->join_event[k]);
+  }
+  for (int k = 0; k < vbt_model::kMaxBranches; ++k)
+    if (m->fork_event[k]) cudaEventDestroy(m->fork_event[k]);
   if (m->dev_data) cudaFree(m->dev_data);
   delete m;
 }

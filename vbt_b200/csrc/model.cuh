@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 5;
+constexpr int kBlobVersion = 6;
 
 struct BlobHeader {
   uint32_t magic;
@@ -72,7 +72,8 @@ struct OpRecord {
   //   out_off(b) + p * out_pix_stride ; out_off(b) = tensor base + b * out_batch_stride
   int32_t out_kind;        // 0 workspace tensor, 1 raw class output, 2 raw box output
   int32_t out_pix_stride;
-  int32_t reserved[7];
+  int32_t branch;          // 0: trunk (program order); k > 0: head chain k, independent of the others
+  int32_t reserved[6];
 };
 static_assert(sizeof(OpRecord) == 224, "op record layout");
 
@@ -93,6 +94,12 @@ struct vbt_model {
   const float* dev_exp_lut = nullptr;
   int kernels_per_detect = 0;
   int device = -1;
+  // side streams for the independent head chains (fork after the trunk, join at the end)
+  static constexpr int kMaxBranches = 16;
+  cudaStream_t branch_stream[kMaxBranches] = {};
+  cudaEvent_t fork_event[kMaxBranches] = {}, join_event[kMaxBranches] = {};
+  int fork_after[kMaxBranches] = {};   // index of the trunk op that produces branch k's input
+  int n_branches = 0;      // highest branch id used by the program
   // CUDA graphs of the layer program, one per (buffers, batch) a caller has used twice
   struct GraphKey {
     const void *in, *ws, *cls, *box; int B;

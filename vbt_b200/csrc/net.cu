@@ -472,7 +472,7 @@ namespace {
 // Enqueue the whole layer program on `st` (one launch per op).  `prof`: event set for the
 // per-op timing mode (bench.py), else nullptr.
 int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int8_t* dev_out_cls,
-            int8_t* dev_out_box, cudaStream_t st, cudaEvent_t* prof) {
+            int8_t* dev_out_box, cudaStream_t main_st, cudaEvent_t* prof) {
   using namespace vbt;
   uint8_t* ws = static_cast<uint8_t*>(dev_workspace);
   const long long Np = m->hdr.n_anchors_pad;
@@ -484,8 +484,18 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
   };
   auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
   int launched = 0;
-  if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], st));
+  // Branch k > 0 (a head chain) runs on its own stream: forked once the trunk is enqueued,
+  // joined at the end.  Under stream capture this becomes parallel branches of the graph.
+  const bool fork = !prof && m->n_branches > 0;
+  bool started[vbt_model::kMaxBranches] = {};
+  if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], main_st));
   for (const OpRecord& op : m->ops) {
+    cudaStream_t st = main_st;
+    if (fork && op.branch > 0) {
+      const int k = op.branch - 1;
+      if (!started[k]) { VBT_CHECK_CUDA(cudaStreamWaitEvent(m->branch_stream[k], m->fork_event[k], 0)); started[k] = true; }
+      st = m->branch_stream[k];
+    }
     switch (op.type) {
       case OP_STEM: {
         StemArgs a;
@@ -569,7 +579,15 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
     }
     ++launched;
     VBT_CHECK_CUDA(cudaPeekAtLastError());
-    if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], st));
+    if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], main_st));
+    if (fork && op.branch == 0)
+      for (int k = 0; k < m->n_branches; ++k)
+        if (m->fork_after[k] == launched - 1) VBT_CHECK_CUDA(cudaEventRecord(m->fork_event[k], main_st));
+  }
+  for (int k = 0; k < vbt_model::kMaxBranches; ++k) {
+    if (!started[k]) continue;
+    VBT_CHECK_CUDA(cudaEventRecord(m->join_event[k], m->branch_stream[k]));
+    VBT_CHECK_CUDA(cudaStreamWaitEvent(main_st, m->join_event[k], 0));
   }
   return VBT_OK;
 }

@@ -273,10 +273,10 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   a.mult = reinterpret_cast<const float*>(m->dev_data + op.scale_off);
   a.M = (long long)B * op.h_in * op.w_in;
   a.cin_p = op.cin_p; a.cout_p = op.cout_p;
-  // Output columns per CTA.  TMEM (512 columns per SM) bounds how many CTAs are resident, and a
-  // CTA is one serial load -> MMA -> epilogue chain, so narrow chunks (more, shorter CTAs in
-  // flight) hide latency better than wide ones; the A tile is re-read from L2 per chunk.
-  static const int nc_max = [] { const char* e = getenv("VBT_PW_NC"); int v = e ? atoi(e) : 64;
+  // Output columns per CTA: as wide as one MMA allows (256).  Narrower chunks put more CTAs
+  // in flight but repeat the per-CTA fixed work (A tile load, TMEM allocation, barriers);
+  // measured on B200 (VBT_PW_NC sweep, profiles/): 128-256 beats 32-96 by 5-20 %.
+  static const int nc_max = [] { const char* e = getenv("VBT_PW_NC"); int v = e ? atoi(e) : 256;
                                  return v < 16 ? 16 : (v > 256 ? 256 : v / 16 * 16); }();
   const int n_chunks = (op.cout_p + nc_max - 1) / nc_max;
   a.nc = ((op.cout_p + n_chunks - 1) / n_chunks + 15) / 16 * 16;

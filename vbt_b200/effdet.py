@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 5
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 6
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -98,6 +98,7 @@ class Op:
     residual: int = -1                       # PW: tensor added after the conv
     out_kind: int = 0                        # 0 workspace, 1 class output, 2 box output
     level_offset: int = 0                    # anchors before this level (head outputs)
+    branch: int = 0                          # 0: trunk; k > 0: independent head chain k
     name: str = ''
     # filled by quantize()
     q: dict = field(default_factory=dict)
@@ -212,13 +213,18 @@ class Graph:
         self.level_sizes = [lvl_hw[l] for l in (3, 4, 5, 6, 7)]
         offs = 0
         for li, l in enumerate((3, 4, 5, 6, 7)):
-            for net, cout, kind in (('cls', a_per * NUM_CLASSES, 1), ('box', a_per * 4, 2)):
+            for ni, (net, cout, kind) in enumerate((('cls', a_per * NUM_CLASSES, 1), ('box', a_per * 4, 2))):
+                first = len(self.ops)
                 x = self.fpn_out[li]
                 for r in range(self.head_rep):
                     x = self._dw(x, 3, 1, False, f'{net}{l}.{r}.dw')
                     x = self._pw(x, C, True, f'{net}{l}.{r}.pw')
                 x = self._dw(x, 3, 1, False, f'{net}{l}.out.dw')
                 self._pw(x, cout, False, f'{net}{l}.out.pw', out_kind=kind, level_offset=offs)
+                # the ten (level, net) chains only read the BiFPN outputs and write disjoint
+                # slices of the raw outputs: independent branches the GPU may run concurrently
+                for op in self.ops[first:]:
+                    op.branch = 1 + li * 2 + ni
             offs += lvl_hw[l][0] * lvl_hw[l][1] * a_per
         self.n_anchors = offs
 
@@ -453,15 +459,23 @@ def quantize(g: Graph, calib_frames):
 
 
 def plan_workspace(g: Graph):
-    """First-fit allocation of per-frame activation offsets with liveness reuse."""
+    """First-fit allocation of per-frame activation offsets with liveness reuse.
+
+    Ops of branch 0 run in program order and recycle memory as tensors die.  Ops of a branch
+    k > 0 (the head chains) may run concurrently with every other branch: their tensors come
+    from a private region that is only recycled within the branch, and a trunk tensor read by
+    any branch is never recycled."""
     last_use = {}
+    keep = set()
     for i, op in enumerate(g.ops):
         for t in op.inputs + ([op.residual] if op.residual >= 0 else []):
             last_use[t] = i
-    free, top = [], 0                     # free: list of (offset, size)
-    sizes = {}
+            if op.branch != 0:
+                keep.add(t)
+    pools = {}                            # branch -> (free list, sizes)
+    top = 0
 
-    def alloc(n):
+    def alloc(free, n):
         nonlocal top
         n = (n + 255) // 256 * 256
         for j, (o, s) in enumerate(free):
@@ -475,7 +489,7 @@ def plan_workspace(g: Graph):
         top += n
         return o, n
 
-    def release(o, n):
+    def release(free, o, n):
         free.append((o, n))
         free.sort()
         merged = []
@@ -486,14 +500,23 @@ def plan_workspace(g: Graph):
                 merged.append((o2, s2))
         free[:] = merged
 
+    owner = {}
     g.tensors[g.input].ws_offset = -1      # the input lives in the caller's buffer
     for i, op in enumerate(g.ops):
+        free, sizes = pools.setdefault(op.branch, ([], {}))
         if op.out >= 0:
             t = g.tensors[op.out]
-            t.ws_offset, sizes[op.out] = alloc(t.bytes_per_frame)
+            t.ws_offset, sizes[op.out] = alloc(free, t.bytes_per_frame)
+            owner[op.out] = op.branch
         for tid in set(op.inputs + ([op.residual] if op.residual >= 0 else [])):
-            if tid != g.input and last_use.get(tid) == i and tid in sizes:
-                release(g.tensors[tid].ws_offset, sizes.pop(tid))
+            if tid == g.input or last_use.get(tid) != i or tid not in owner:
+                continue
+            b = owner[tid]
+            if b == 0 and tid in keep:
+                continue                   # read by a concurrent branch: stays until the end
+            if b == op.branch:
+                bfree, bsizes = pools[b]
+                release(bfree, g.tensors[tid].ws_offset, bsizes.pop(tid))
     g.ws_bytes_per_frame = top
     return top
 
@@ -508,7 +531,7 @@ def _pack_op(rec):
     out += struct.pack('<5q', f['w_off'], f['bias_off'], f['scale_off'], f['lut_off'],
                        f['out_elem_offset'])
     out += struct.pack('<3i i 3i 3i 3i ii 7i', *f['add_mult'], f['add_shift'], *f['resample'],
-                       *f['in_h'], *f['in_w'], f['out_kind'], f['out_pix_stride'], *([0] * 7))
+                       *f['in_h'], *f['in_w'], f['out_kind'], f['out_pix_stride'], f['branch'], *([0] * 6))
     return out
 
 
@@ -517,7 +540,7 @@ OP_RECORD_BYTES = len(_pack_op(dict(
     h_in=0, w_in=0, h_out=0, w_out=0, zp_in=[0, 0, 0], zp_out=0, act_lo=0, act_hi=0, pad_top=0,
     pad_left=0, w_off=0, bias_off=0, scale_off=0, lut_off=0, add_mult=[0, 0, 0], add_shift=0,
     resample=[0, 0, 0], in_h=[0, 0, 0], in_w=[0, 0, 0], out_kind=0, out_pix_stride=0,
-    out_elem_offset=0)))
+    out_elem_offset=0, branch=0)))
 
 
 def pack_blob(g: Graph):
@@ -555,7 +578,7 @@ def pack_blob(g: Graph):
                  zp_out=q['zp_out'], act_lo=q['act_lo'], act_hi=q['act_hi'],
                  pad_top=0, pad_left=0, w_off=-1, bias_off=-1, scale_off=-1, lut_off=-1,
                  add_mult=[0, 0, 0], add_shift=0, out_kind=op.out_kind,
-                 out_pix_stride=cout_p, out_elem_offset=0)
+                 out_pix_stride=cout_p, out_elem_offset=0, branch=op.branch)
         r['in'] = (op.inputs + [-1, -1, -1])[:3]
         r['zp_in'] = (q['zp_in'] + [0, 0, 0])[:3]
         r['resample'] = (list(op.resample) + [0, 0, 0])[:3]
