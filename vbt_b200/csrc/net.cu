@@ -164,20 +164,23 @@ __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
   const int4 bias = __ldg(reinterpret_cast<const int4*>(a.bias) + cw);
   const float4 mult = __ldg(reinterpret_cast<const float4*>(a.mult) + cw);
   const uint32_t zpw = (uint32_t)(a.zp_in & 0xff) * 0x01010101u;
-  const uint32_t* in = reinterpret_cast<const uint32_t*>(a.in) + cw;
-  uint32_t* out = reinterpret_cast<uint32_t*>(a.out) + cw;
-  const size_t words = (size_t)a.words;
+  // All addressing is a warp-uniform base pointer + a 32-bit word offset (tensors are far
+  // below 2^32 words), so a load costs one integer add and the LDG itself.
+  const uint32_t* __restrict__ in = reinterpret_cast<const uint32_t*>(a.in);
+  uint32_t* __restrict__ out = reinterpret_cast<uint32_t*>(a.out);
+  const uint32_t words = (uint32_t)a.words;
+  const uint32_t row_words = (uint32_t)a.W * words;
   vbt::pdl_wait();
   vbt::pdl_launch_dependents();
 
-  for (long long item = (long long)blockIdx.x * il_n + il; item < a.n_items;
-       item += (long long)gridDim.x * il_n) {
-    const int seg = (int)(item % a.n_seg);
-    long long r = item / a.n_seg;
-    const int oy = (int)(r % a.Ho), b = (int)(r / a.Ho);
+  const int n_items = (int)a.n_items;                 // < 2^31: 32-bit index arithmetic
+  for (int item = blockIdx.x * il_n + il; item < n_items; item += gridDim.x * il_n) {
+    const int seg = item % a.n_seg;
+    const int r = item / a.n_seg;
+    const int oy = r % a.Ho, b = r / a.Ho;
     const int x0 = seg * a.seg_len, x1 = min(x0 + a.seg_len, a.Wo);
-    const uint32_t* fin = in + (size_t)b * a.H * a.W * words;
-    const uint32_t* rowp[K];
+    const uint32_t frame = (uint32_t)b * (uint32_t)a.H * row_words + (uint32_t)cw;
+    uint32_t row_off[K];
     bool row_ok[K];
     bool rows_in = true;
 #pragma unroll
@@ -185,31 +188,31 @@ __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
       const int iy = oy * S - a.pad_top + ky;
       row_ok[ky] = iy >= 0 && iy < a.H;
       rows_in = rows_in && row_ok[ky];
-      rowp[ky] = fin + (size_t)(row_ok[ky] ? iy : 0) * a.W * words;
+      row_off[ky] = frame + (uint32_t)(row_ok[ky] ? iy : 0) * row_words;
     }
     // J outputs per group: all (J-1)*S+K window columns are loaded first (independent loads in
     // flight together), then the J outputs are computed from registers
-    uint32_t* orow = out + (((size_t)b * a.Ho + oy) * a.Wo) * words;
+    uint32_t out_off = (((uint32_t)b * a.Ho + oy) * a.Wo + x0) * words + (uint32_t)cw;
     for (int xg = x0; xg < x1; xg += J) {
       uint32_t win[NCOL][K];
       const int ixb = xg * S - a.pad_left;
       if (rows_in && ixb >= 0 && ixb + NCOL <= a.W) {       // interior: no predicates
-        int idx = ixb * a.words;
+        uint32_t col = (uint32_t)ixb * words;
 #pragma unroll
         for (int c = 0; c < NCOL; ++c) {
 #pragma unroll
-          for (int ky = 0; ky < K; ++ky) win[c][ky] = __ldg(rowp[ky] + idx);
-          idx += a.words;
+          for (int ky = 0; ky < K; ++ky) win[c][ky] = __ldg(in + (row_off[ky] + col));
+          col += words;
         }
       } else {                                              // image border: zero-point padding
 #pragma unroll
         for (int c = 0; c < NCOL; ++c) {
           const int ix = ixb + c;
           const bool col_ok = ix >= 0 && ix < a.W;
-          const int idx = (col_ok ? ix : 0) * a.words;
+          const uint32_t col = (uint32_t)(col_ok ? ix : 0) * words;
 #pragma unroll
           for (int ky = 0; ky < K; ++ky) {
-            const uint32_t v = __ldg(rowp[ky] + idx);
+            const uint32_t v = __ldg(in + (row_off[ky] + col));
             win[c][ky] = (col_ok && row_ok[ky]) ? v : zpw;
           }
         }
@@ -234,9 +237,10 @@ __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
               acc3 = __dp4a(xv, (int)wv.w, acc3);
             }
           }
-          orow[(size_t)x * words] = vbt::pack4_s8(a.rq(acc0, mult.x), a.rq(acc1, mult.y),
-                                                  a.rq(acc2, mult.z), a.rq(acc3, mult.w));
+          out[out_off] = vbt::pack4_s8(a.rq(acc0, mult.x), a.rq(acc1, mult.y),
+                                       a.rq(acc2, mult.z), a.rq(acc3, mult.w));
         }
+        out_off += words;
       }
     }
   }
