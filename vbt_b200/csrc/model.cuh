@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 6;
+constexpr int kBlobVersion = 7;
 
 struct BlobHeader {
   uint32_t magic;
@@ -60,7 +60,8 @@ struct OpRecord {
   int32_t zp_out;
   int32_t act_lo, act_hi;  // clamp of the int8 result
   int32_t pad_top, pad_left;
-  int64_t w_off, bias_off, scale_off, lut_off;   // data-section byte offsets (-1 none)
+  int64_t w_off, bias_off, scale_off, lut_off;   // data-section byte offsets (-1 none); DW: lut_off =
+                                                 // block-diagonal tensor-core weights (dw_umma.cu)
   int64_t out_elem_offset; // within-frame element offset (level offset for the heads)
   // OP_ADD / fused residual: integer rescale  out = clamp(((sum_i (x_i - zp_i)*mult_i)
   //                                             + round) >> shift) + zp_out)

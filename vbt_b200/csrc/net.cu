@@ -22,6 +22,8 @@ namespace vbt {
 cudaEvent_t* profile_begin(vbt_model* m);
 int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res,
                    int8_t* out, long long out_batch_stride, int B, cudaStream_t st, bool* taken);
+int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int8_t* out, int B,
+                   cudaStream_t st, bool* taken);
 }
 
 namespace {
@@ -515,6 +517,9 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         break;
       }
       case OP_DW: {
+        bool dw_taken = false;
+        if (int rc = launch_dw_umma(m, op, tensor_ptr(op.in[0]), tensor_ptr(op.out), B, st, &dw_taken)) return rc;
+        if (dw_taken) break;
         DwArgs a;
         a.in = tensor_ptr(op.in[0]); a.out = tensor_ptr(op.out);
         a.w = reinterpret_cast<const uint32_t*>(data(op.w_off));

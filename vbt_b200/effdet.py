@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 6
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 7
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -521,6 +521,25 @@ def plan_workspace(g: Graph):
     return top
 
 
+def dw_diag_blocks(w_q, c_p):
+    """Depthwise weights as block-diagonal tensor-core operands (vbt_b200/csrc/dw_umma.cu).
+
+    For every pair of 16-channel groups and every tap: a [32 out][32 in] int8 matrix whose
+    diagonal holds the 32 tap weights, in the K-major no-swizzle core-matrix layout the MMA
+    reads (byte (n, k) at (k // 16) * 512 + (n // 8) * 128 + (n % 8) * 16 + k % 16).
+    w_q: int8 [c, k, k].  Returns int8 [pairs, k*k, 1024]."""
+    c, k, _ = w_q.shape
+    pairs = (c_p // 16 + 1) // 2
+    wt = np.zeros((pairs * 32, k * k), np.int8)
+    wt[:c] = w_q.reshape(c, k * k)
+    out = np.zeros((pairs, k * k, 1024), np.int8)
+    n = np.arange(32)
+    off = (n // 16) * 512 + (n // 8) * 128 + (n % 8) * 16 + n % 16
+    for p in range(pairs):
+        out[p][:, off] = wt[p * 32:(p + 1) * 32].T
+    return out
+
+
 def _pack_op(rec):
     """OpRecord (vbt_b200/csrc/model.cuh), little endian."""
     f = rec
@@ -625,6 +644,8 @@ def pack_blob(g: Graph):
                 r['zp_in'][2] = q['zp_out']
             if 'lut' in q:
                 r['lut_off'] = put(q['lut'])
+            if op.type == OP_DW:
+                r['lut_off'] = put(dw_diag_blocks(q['w'], cout_p))
         elif op.type == OP_ADD:
             r['add_mult'] = (q['add_mult'] + [0, 0, 0])[:3]
             r['add_shift'] = q['add_shift']
