@@ -55,3 +55,23 @@ def test_pointwise_residual(h, w, c, cmid, B):
 @pytest.mark.parametrize('act', [False, True])
 def test_depthwise(h, w, c, k, stride, B, act):
     check(MG.dw_graph(h, w, c, k, stride, act=act, seed=h * 100 + c), B)
+
+
+@pytest.mark.parametrize('impl', ['simt', 'umma'])
+def test_depthwise_both_implementations(impl):
+    """The two depthwise implementations -- tensor-pipe implicit GEMM with block-diagonal
+    weights (dw_umma.cu) and channel-word-stationary dp4a (net.cu) -- forced in turn for every
+    kernel size / stride against the oracle.  VBT_DW_IMPL is read once per process, hence the
+    subprocess."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_ops as T; '
+            'import micrograph as MG\n'
+            'for (h, w, c, k, s, B) in [(17, 13, 96, 3, 2, 3), (16, 16, 144, 5, 2, 2), (9, 11, 240, 5, 1, 2), '
+            '(40, 40, 40, 3, 1, 1), (33, 31, 16, 3, 2, 1), (7, 7, 1152, 3, 1, 2), (160, 160, 32, 3, 1, 1)]:\n'
+            '    T.check(MG.dw_graph(h, w, c, k, s, act=True, seed=h), B)\n' % (os.path.dirname(here), here))
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, VBT_DW_IMPL=impl),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]

@@ -223,6 +223,11 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
   static const bool enabled = [] { const char* e = getenv("VBT_DW_IMPL"); return !(e && e[0] == 's'); }();
   *taken = false;
   if (!enabled || op.lut_off < 0 || (op.k != 3 && op.k != 5) || (op.stride != 1 && op.stride != 2)) return VBT_OK;
+  // Measured on B200 (profiles/, per-op timings): the tensor-pipe form wins 1.5-2x for 5x5 taps
+  // (25 MMAs replace 100 dp4a per output word); for 3x3 the channel-word-stationary SIMT kernel
+  // in net.cu is as fast or faster, so it keeps those unless VBT_DW_IMPL=umma forces this one.
+  static const bool force = [] { const char* e = getenv("VBT_DW_IMPL"); return e && e[0] == 'u'; }();
+  if (op.k == 3 && !force) return VBT_OK;
   DwUArgs a;
   a.in = in; a.out = out;
   a.wdiag = reinterpret_cast<const int8_t*>(m->dev_data + op.lut_off);
@@ -237,8 +242,10 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
   // positions per CTA: small CTAs (2-4 tiles) keep 4-8 of them resident per SM, which hides the
   // serial load -> MMA -> epilogue chain of each far better than two 8-tile CTAs do
   static const int pos_env = [] { const char* e = getenv("VBT_DW_POS"); return e ? atoi(e) : 256; }();
-  const int max_pos = std::max(128, std::min(1024, pos_env)) / (op.stride == 1 ? 1 : 2);
-  a.TH = std::max(1, std::min(op.h_out, max_pos / a.PW));
+  const int max_pos = std::max(128, std::min(1024, pos_env));
+  // ... but a band re-reads K-S input rows, so never fewer than 4 output rows per band
+  a.TH = std::max(std::min(op.h_out, 4), std::min(op.h_out, max_pos / a.PW));
+  while (a.TH > 1 && (a.TH * a.PW + 127) / 128 > kMaxTiles) --a.TH;
   a.n_bands = (op.h_out + a.TH - 1) / a.TH;
   a.n_mt = (a.TH * a.PW + 127) / 128;
   if (a.n_mt > kMaxTiles) return VBT_OK;                   // a single row wider than the tile budget
