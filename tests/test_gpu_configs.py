@@ -1,0 +1,165 @@
+"""The BASELINE.json configurations as parity cases on a B200:
+
+  configs[0/1]  track.py pipeline on one synthetic clip (Lite0), through the CLI's `track()` and the
+                pickled DataFrame that plot.py consumes;
+  configs[2]    Lite1 384x384 detection + tracking at frame batch 256;
+  configs[3]    Lite2 448x448 at frame batch 256 (int8);
+  configs[4]    many videos sharded by whole videos + one gather of the track tables.
+
+At full batch the CPU oracle would take minutes, so exactness is carried by a size-independent
+property -- a frame's result does not depend on the batch it travels in -- checked over the
+whole batch against small batches, which in turn are checked against the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import effdet as OE, ocsort as oo, postprocess as OP, resize as OR, velocity as ov
+
+pytestmark = pytest.mark.gpu
+
+_graphs = {}
+
+
+def graph(variant):
+    if variant not in _graphs:
+        from vbt_b200 import effdet
+        _graphs[variant] = effdet.build_synthetic(variant)
+    return _graphs[variant]
+
+
+def oracle_rows(g, frames, fps, thr, numbers=None):
+    imgs = OR.preprocess_batch(frames, g.S, swap_rb=True)
+    cls, box, _ = OE.run(g, imgs)
+    a = g.anchors()
+    dets = []
+    for b in range(len(frames)):
+        ob, oc, osc, cnt, _ = OP.detection_postprocess(cls[b], box[b], a, g.box_scale, g.box_zp)
+        dets.append(OP.tracker_inputs(OP.detect_results(ob, osc, cnt, thr)).reshape(-1, 6))
+    return oo.track_rows(dets, fps, max_age=30, iou_threshold=0.1, frame_numbers=numbers)
+
+
+def synthetic_frames(n, h, w, seed):
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    return np.stack([np.roll(base, 4 * i, axis=1) for i in range(n)])
+
+
+def test_config1_track_cli_on_a_synthetic_clip(tmp_path):
+    """cv2-decoded clip -> track() -> DataFrame pickle with the reference's schema and file name
+    -> the plot.py analysis; rows equal the CPU oracle chain on the same decoded frames."""
+    import cv2
+    import pandas as pd
+    from vbt_b200.interpreter import Interpreter
+    from vbt_b200.pipeline import COLUMNS, export_dataframe
+    from vbt_b200.track import track
+    from vbt_b200.velocity import smooth_and_analyze
+    g = graph('lite0')
+    path = str(tmp_path / '007_squat_3reps.avi')
+    frames = synthetic_frames(12, 240, 320, seed=5)
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*'MJPG'), 30.0, (320, 240))
+    assert wr.isOpened()
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    cap = cv2.VideoCapture(path)
+    fps = cap.get(cv2.CAP_PROP_FPS)
+    decoded = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        decoded.append(f)
+    cap.release()
+    decoded = np.stack(decoded)
+    interp = Interpreter(model_path=g, num_threads=4)
+    interp.allocate_tensors()
+    thr = 0.3
+    data = track(path, interp, thr, frame_stride=1, batch=8)
+    assert list(data) == COLUMNS                                   # key order (track.py:144-145)
+    want = oracle_rows(g, decoded, fps, thr)
+    got = np.column_stack([np.asarray(data[c], dtype=np.float64) for c in COLUMNS])
+    assert len(want) > 0 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    # HEAD's stride: every 16th frame only (track.py:166) -> frame 16 does not exist in a 12-frame clip
+    assert len(track(path, interp, thr)['id']) == 0
+    df, out = export_dataframe(data, path, 'models/efficientdet_lite0_whole.tflite', str(tmp_path))
+    assert os.path.basename(out).startswith('007_squat_3reps_id') and out.endswith('_efficientdet_lite0_whole.pkl.gz')
+    back = pd.read_pickle(out)
+    assert list(back.columns) == COLUMNS and back['id'].dtype == np.int64
+    assert back[['id', 'time']].values.tolist() == sorted(back[['id', 'time']].values.tolist())
+    tid = int(os.path.basename(out).split('_id')[1].split('_')[0])
+    phases = smooth_and_analyze(back, tid, 0.45)
+    sel = back[back['id'] == tid].drop(columns=['id']).to_numpy(dtype=np.float64)
+    want_ph = ov.analyze_series(sel, 0.45)
+    got_ph = np.array([[p.time_start, p.time_end, p.y_start, p.y_end, p.rom, p.type] for p in phases]).reshape(-1, 6)
+    assert np.array_equal(got_ph, want_ph)
+
+
+@pytest.mark.parametrize('variant,cfg', [('lite1', 'configs[2]'), ('lite2', 'configs[3]')])
+def test_batch_256_detection_and_tracking(variant, cfg):
+    import torch
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    g = graph(variant)
+    n, thr = 256, 0.3
+    frames = synthetic_frames(n, 135, 240, seed=9)
+    dev = torch.as_tensor(frames, device='cuda')
+    big = Detector(g, max_batch=256)
+    small = Detector(g, max_batch=8)
+    # (a) one launch set over 256 frames == 32 launch sets over 8 frames, raw outputs bit for bit
+    big.network(big.preprocess(dev, True))
+    cls_big = big.raw_cls[:n, :g.n_anchors].cpu().numpy()
+    box_big = big.raw_box[:n, :g.n_anchors].cpu().numpy()
+    for s in range(0, n, 8):
+        small.network(small.preprocess(dev[s:s + 8], True))
+        assert np.array_equal(small.raw_cls[:8, :g.n_anchors].cpu().numpy(), cls_big[s:s + 8]), (cfg, s)
+        assert np.array_equal(small.raw_box[:8, :g.n_anchors].cpu().numpy(), box_big[s:s + 8]), (cfg, s)
+    # (b) the small batch is the oracle's: first and last frames
+    pick = [0, 1, n - 1]
+    imgs = OR.preprocess_batch(frames[pick], g.S, swap_rb=True)
+    want_cls, want_box, _ = OE.run(g, imgs)
+    assert np.array_equal(cls_big[pick], want_cls) and np.array_equal(box_big[pick], want_box)
+    # (c) tracking + velocity over the 256-frame batch == the same clip in batches of 8
+    numbers = torch.arange(1, n + 1, dtype=torch.int32, device='cuda')
+    p_big = VideoPipeline(big, 30.0, thr, row_cap=1 << 14)
+    p_big.process(dev, numbers, swap_rb=True)
+    r_big = p_big.finish()
+    p_small = VideoPipeline(small, 30.0, thr, row_cap=1 << 14)
+    for s in range(0, n, 8):
+        p_small.process(dev[s:s + 8], numbers[s:s + 8], swap_rb=True)
+    r_small = p_small.finish()
+    assert len(r_big['rows']) > 0
+    assert np.array_equal(r_big['rows'], r_small['rows'])
+    assert sorted(r_big['phases']) == sorted(r_small['phases'])
+    for tid in r_big['phases']:
+        a = [(p.time_start, p.time_end, p.rom, p.type) for p in r_big['phases'][tid]]
+        b = [(p.time_start, p.time_end, p.rom, p.type) for p in r_small['phases'][tid]]
+        assert a == b
+
+
+def test_config4_videos_sharded_and_gathered():
+    """Several clips of different lengths through shard.track_videos (one rank here; the
+    multi-rank plan and gather are covered on CPU by tests/test_shard_gloo.py): per-video tables
+    equal the oracle chain, tracker state never leaks from one video into the next."""
+    import torch
+    from vbt_b200 import shard
+    from vbt_b200.interpreter import Detector
+    g = graph('lite0')
+    det = Detector(g, max_batch=4)
+    lens = [5, 9, 3, 7]
+    vids = [{'fps': 30.0 if i % 2 == 0 else 60.0,
+             'frames': torch.as_tensor(synthetic_frames(n, 135, 240, seed=20 + i), device='cuda')}
+            for i, n in enumerate(lens)]
+    thr = 0.3
+    tables, phases = shard.track_videos(vids, det, detection_threshold=thr, row_cap=4096)
+    assert sorted(tables) == list(range(len(lens)))
+    for i, v in enumerate(vids):
+        want = oracle_rows(g, v['frames'].cpu().numpy(), v['fps'], thr)
+        assert tables[i].shape == want.shape, i
+        assert np.array_equal(tables[i], want), i
+    # frame stride (HEAD's `frame_count % 16`, here 2): frames 2, 4, 6, ... keep their numbers
+    t2, _ = shard.track_videos(vids[1:2], det, detection_threshold=thr, frame_stride=2, row_cap=4096)
+    f = vids[1]['frames'].cpu().numpy()
+    want = oracle_rows(g, f[1::2], 60.0, thr, numbers=list(range(2, 10, 2)))
+    assert np.array_equal(t2[0], want)

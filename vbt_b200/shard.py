@@ -68,3 +68,45 @@ def gather_row_tables(local_tables, n_videos, device=None, group=None):
     for k in range(n_videos):
         out.setdefault(k, np.zeros((0, 8)))
     return out
+
+
+def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank=None, world=None,
+                 group=None, **pipe_kw):
+    """Run the hot path over many videos, sharded by whole videos across the ranks.
+
+    videos: list of dicts ``{'fps': float, 'frames': uint8 [N,H,W,3] CUDA or pinned-host tensor}``
+    (BGR, as decoded).  Each rank processes the videos `lpt_assign` gives it with one
+    `VideoPipeline` (tracker and velocity state reset per video, like the fresh interpreter and
+    tracker per source of track.py:88-101,157), then ONE gather makes every row table visible on
+    every rank.  Returns ``(tables, phases)``: tables = {video index: float64 [n,8]} for all
+    videos, phases = {video index: {id: [Phase]}} for this rank's videos."""
+    import torch
+    import torch.distributed as dist
+    from .pipeline import VideoPipeline
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    plan = lpt_assign([int(v['frames'].shape[0]) // frame_stride for v in videos], world)
+    pipe = None
+    local, phases = {}, {}
+    B = detector.max_batch
+    for vi in plan[rank]:
+        v = videos[vi]
+        if pipe is None:
+            pipe = VideoPipeline(detector, v['fps'], detection_threshold, **pipe_kw)
+        pipe.reset(v['fps'])
+        frames = v['frames']
+        n = int(frames.shape[0])
+        # 1-based frame_count of the kept frames (track.py:161,166)
+        keep = torch.arange(frame_stride, n + 1, frame_stride, dtype=torch.int32)
+        numbers = keep.to('cuda')
+        for s in range(0, len(keep), B):
+            idx = keep[s:s + B].long() - 1
+            chunk = frames[idx[0]:idx[-1] + 1] if frame_stride == 1 else frames[idx.to(frames.device)]
+            pipe.process(chunk.contiguous(), numbers[s:s + B], swap_rb=True)
+        res = pipe.finish()
+        local[vi] = res['rows']
+        phases[vi] = res['phases']
+    tables = gather_row_tables(local, len(videos), group=group)
+    return tables, phases
