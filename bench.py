@@ -380,9 +380,10 @@ def main():
         main_stream = torch.cuda.current_stream()
         d2h_bytes = res_host.numel() * 4
 
-        # K1 reads the pinned host frames in place (zero copy): per output row it pulls the two
-        # source rows it needs over PCIe, so 2*S of the H rows cross the bus instead of all H.
-        h2d_bytes = B * 2 * g.S * W * 3
+        # Row-sparse ingest (vbt_b200/ingest.py): per batch, 16 strided DMA copies move only the
+        # source rows the resize reads (2*S of the H rows) from pinned host memory.
+        ing = pipe.use_row_sparse_ingest(H, W)
+        h2d_bytes = B * ing.bytes_per_frame
 
         def e2e_step(i):
             slot = i % ring
@@ -452,8 +453,8 @@ def main():
                 'cache': 'inputs larger than L2: 398 MB of frames per step vs 126 MB L2, no flush needed',
                 'pipeline': f'{len(pipe.detectors)} detection lanes (stream + CUDA graph each), tracker/velocity '
                             'on a side stream; per-kernel times from a second single-lane pass with per-op events',
-                'e2e_source': 'ring of 3 pinned host batches read in place by K1 over PCIe (zero copy: the 2*S '
-                              'source rows per frame the resize touches), per-step D2H of the packed '
+                'e2e_source': 'ring of 3 pinned host batches; per step a row-sparse H2D DMA (only the 2*S source '
+                              'rows per frame the resize reads) on an ingest stream, and a D2H of the packed '
                               'detection table + row count',
                 'parallelism': f'{world} video shard(s), one per GPU, NCCL gather of row tables at the end',
             },

@@ -50,6 +50,22 @@ long long vbt_launch_count(void);
 int vbt_preprocess_u8(const uint8_t* dev_frames, int B, int H, int W, int swap_rb,
                       uint8_t* dev_out, int S, void* stream);
 
+/* Row-sparse ingest of host frames (replaces the host->device half of the same call sites:
+ * the reference resizes on the host, so only the resized image ever moves; here only the
+ * source rows the bilinear kernel touches cross PCIe -- 2*S of H, e.g. 16 of every 27 rows
+ * for 1080 -> 320).
+ * vbt_copy_rows_h2d: host_frames u8 [B,H,W,3] in PINNED host memory; the touched rows repeat
+ * with `period` = H / gcd(H,S) source rows; host_rows[n_rows] are the touched row indices
+ * inside one period.  Issues n_rows strided DMA copies (cudaMemcpy2DAsync) on `stream` into
+ * dev_rows u8 [B * H/period, n_rows, W*3].
+ * vbt_preprocess_rows_u8: K1 over that table; dev_row_map i32 [H] maps a source row to its
+ * table row within the frame (rows_per_frame = H/period * n_rows). */
+int vbt_copy_rows_h2d(const uint8_t* host_frames, int B, int H, int W, int period,
+                      const int32_t* host_rows, int n_rows, uint8_t* dev_rows, void* stream);
+int vbt_preprocess_rows_u8(const uint8_t* dev_rows, int B, int H, int W, int rows_per_frame,
+                           const int32_t* dev_row_map, int swap_rb, uint8_t* dev_out, int S,
+                           void* stream);
+
 /* ---- K2-K5 the EfficientDet-Lite network ------------------------------------------
  * replaces: tflite_runtime Interpreter(model_path) / allocate_tensors (track.py:93-94)
  * and the graph part of signature_fn(images=...) (odt.py:58-61).

@@ -55,6 +55,31 @@ def test_preprocess_reads_pinned_host_frames_in_place():
     assert np.array_equal(out.cpu().numpy(), OR.preprocess_batch(frames, 320, swap_rb=True))
 
 
+@pytest.mark.parametrize('S', [320, 384, 448])
+def test_row_sparse_ingest_equals_full_frames(S):
+    """Host frames sent row-sparse (only the rows the resize reads, strided DMA) give the same
+    K1 output as the full frames; the plan moves 2*S of the 1080 rows."""
+    import torch
+    from vbt_b200 import _lib
+    from vbt_b200.ingest import RowSparseIngest, touched_rows
+    rng = np.random.default_rng(S)
+    frames = rng.integers(0, 256, size=(3, 1080, 1920, 3), dtype=np.uint8)
+    host = torch.from_numpy(frames).pin_memory()
+    ing = RowSparseIngest(4, 1080, 1920, S)
+    assert ing.rows_per_frame == len(touched_rows(1080, S)) == 2 * S
+    out = torch.empty((3, S, S, 3), dtype=torch.uint8, device='cuda')
+    for _ in range(4):                      # cycles through the table ring
+        table, n, slot, ready = ing.upload(host)
+        torch.cuda.current_stream().wait_event(ready)
+        _lib.check(_lib.lib().vbt_preprocess_rows_u8(table.data_ptr(), n, 1080, 1920, ing.rows_per_frame,
+                                                     ing.row_map.data_ptr(), 1, out.data_ptr(), S,
+                                                     _lib.stream_ptr()))
+        ing.free[slot] = torch.cuda.Event()
+        ing.free[slot].record()
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), OR.preprocess_batch(frames, S, swap_rb=True))
+
+
 def test_preprocess_image_helper_matches_oracle():
     from vbt_b200.odt import preprocess_image
     rng = np.random.default_rng(1)

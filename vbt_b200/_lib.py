@@ -42,6 +42,8 @@ PROTOTYPES = {
     'vbt_last_error': (C.c_char_p, []),
     'vbt_launch_count': (C.c_longlong, []),
     'vbt_preprocess_u8': (_I, [_P, _I, _I, _I, _I, _P, _I, _P]),
+    'vbt_copy_rows_h2d': (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _P]),
+    'vbt_preprocess_rows_u8': (_I, [_P, _I, _I, _I, _I, _P, _I, _P, _I, _P]),
     'vbt_model_create': (_I, [_P, _SZ, C.POINTER(_P)]),
     'vbt_model_destroy': (None, [_P]),
     'vbt_model_info': (_I, [_P, C.POINTER(C.c_longlong)]),

@@ -76,9 +76,11 @@ constexpr int kStages = 2;
 
 // Persistent CTAs walk output rows (b, oy).  Row bytes must be a multiple of 16 and the
 // frame base 16-byte aligned (true for W*3 % 16 == 0, e.g. 1920x1080): TMA path.
+// row_map != nullptr: `frames` is a compacted row table ([B][rows_pf][W*3], only the rows the
+// resize touches, see vbt_copy_rows_h2d) and row_map[y] is the table row of source row y.
 __global__ void __launch_bounds__(kThreads) preprocess_tma_kernel(
     const uint8_t* __restrict__ frames, int B, int H, int W, int swap_rb,
-    uint8_t* __restrict__ out, int S) {
+    uint8_t* __restrict__ out, int S, const int32_t* __restrict__ row_map, int rows_pf) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[kStages];
   const int row_bytes = W * 3;
@@ -96,11 +98,13 @@ __global__ void __launch_bounds__(kThreads) preprocess_tma_kernel(
   auto issue = [&](int row, int stage) {
     const int b = row / S, oy = row % S;
     const Interp iy = interp_of(oy, sy, H);
-    const uint8_t* base = frames + (size_t)b * H * row_bytes;
+    const uint8_t* base = frames + (size_t)b * (row_map ? rows_pf : H) * row_bytes;
+    const int r_lo = row_map ? __ldg(row_map + iy.lo) : iy.lo;
+    const int r_hi = row_map ? __ldg(row_map + iy.hi) : iy.hi;
     unsigned char* dst = smem + (size_t)stage * stage_bytes;
     mbar_expect_tx(&full[stage], (uint32_t)stage_bytes);
-    bulk_g2s(dst, base + (size_t)iy.lo * row_bytes, (uint32_t)row_bytes, &full[stage]);
-    bulk_g2s(dst + row_bytes, base + (size_t)iy.hi * row_bytes, (uint32_t)row_bytes, &full[stage]);
+    bulk_g2s(dst, base + (size_t)r_lo * row_bytes, (uint32_t)row_bytes, &full[stage]);
+    bulk_g2s(dst + row_bytes, base + (size_t)r_hi * row_bytes, (uint32_t)row_bytes, &full[stage]);
   };
 
   int it = 0;
@@ -161,12 +165,8 @@ __global__ void preprocess_direct_kernel(const uint8_t* __restrict__ frames, int
 
 }  // namespace
 
-extern "C" int vbt_preprocess_u8(const uint8_t* dev_frames, int B, int H, int W, int swap_rb,
-                                 uint8_t* dev_out, int S, void* stream) {
-  VBT_REQUIRE(dev_frames && dev_out, "vbt_preprocess_u8: null pointer");
-  VBT_REQUIRE(B > 0 && H > 0 && W > 0 && S > 0, "vbt_preprocess_u8: B=%d H=%d W=%d S=%d", B, H, W, S);
-  if (int rc = vbt::ensure_device()) return rc;
-  cudaStream_t st = (cudaStream_t)stream;
+static int launch_preprocess(const uint8_t* dev_frames, int B, int H, int W, int swap_rb, uint8_t* dev_out,
+                             int S, const int32_t* dev_row_map, int rows_pf, cudaStream_t st) {
   const int row_bytes = W * 3;
   const size_t smem = (size_t)kStages * 2 * row_bytes;
   const bool tma_ok = (row_bytes % 16 == 0) && (((size_t)H * row_bytes) % 16 == 0) &&
@@ -186,12 +186,50 @@ extern "C" int vbt_preprocess_u8(const uint8_t* dev_frames, int B, int H, int W,
     const int per_sm = (int)((200 * 1024) / (smem + 1024));
     int grid = sms * (per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm));
     if (grid > B * S) grid = B * S;
-    preprocess_tma_kernel<<<grid, kThreads, smem, st>>>(dev_frames, B, H, W, swap_rb, dev_out, S);
+    preprocess_tma_kernel<<<grid, kThreads, smem, st>>>(dev_frames, B, H, W, swap_rb, dev_out, S,
+                                                        dev_row_map, rows_pf);
   } else {
+    VBT_REQUIRE(dev_row_map == nullptr, "vbt_preprocess_rows_u8: rows of %d bytes are not 16-byte multiples",
+                row_bytes);
     const size_t total = (size_t)B * S * S;
     preprocess_direct_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(dev_frames, B, H, W,
                                                                              swap_rb, dev_out, S);
   }
   VBT_LAUNCHED(1);
+  return VBT_OK;
+}
+
+extern "C" int vbt_preprocess_u8(const uint8_t* dev_frames, int B, int H, int W, int swap_rb,
+                                 uint8_t* dev_out, int S, void* stream) {
+  VBT_REQUIRE(dev_frames && dev_out, "vbt_preprocess_u8: null pointer");
+  VBT_REQUIRE(B > 0 && H > 0 && W > 0 && S > 0, "vbt_preprocess_u8: B=%d H=%d W=%d S=%d", B, H, W, S);
+  if (int rc = vbt::ensure_device()) return rc;
+  return launch_preprocess(dev_frames, B, H, W, swap_rb, dev_out, S, nullptr, 0, (cudaStream_t)stream);
+}
+
+extern "C" int vbt_preprocess_rows_u8(const uint8_t* dev_rows, int B, int H, int W, int rows_per_frame,
+                                      const int32_t* dev_row_map, int swap_rb, uint8_t* dev_out, int S,
+                                      void* stream) {
+  VBT_REQUIRE(dev_rows && dev_row_map && dev_out, "vbt_preprocess_rows_u8: null pointer");
+  VBT_REQUIRE(B > 0 && H > 0 && W > 0 && S > 0 && rows_per_frame > 0,
+              "vbt_preprocess_rows_u8: B=%d H=%d W=%d S=%d rows=%d", B, H, W, S, rows_per_frame);
+  if (int rc = vbt::ensure_device()) return rc;
+  return launch_preprocess(dev_rows, B, H, W, swap_rb, dev_out, S, dev_row_map, rows_per_frame,
+                           (cudaStream_t)stream);
+}
+
+extern "C" int vbt_copy_rows_h2d(const uint8_t* host_frames, int B, int H, int W, int period,
+                                 const int32_t* host_rows, int n_rows, uint8_t* dev_rows, void* stream) {
+  VBT_REQUIRE(host_frames && host_rows && dev_rows, "vbt_copy_rows_h2d: null pointer");
+  VBT_REQUIRE(B > 0 && H > 0 && W > 0 && period > 0 && H % period == 0 && n_rows > 0 && n_rows <= period,
+              "vbt_copy_rows_h2d: B=%d H=%d W=%d period=%d rows=%d", B, H, W, period, n_rows);
+  const size_t row_bytes = (size_t)W * 3;
+  const size_t periods = (size_t)(H / period) * B;     // frames are contiguous: one long 2-D array
+  for (int j = 0; j < n_rows; ++j) {
+    VBT_REQUIRE(host_rows[j] >= 0 && host_rows[j] < period, "vbt_copy_rows_h2d: row %d outside the period", host_rows[j]);
+    VBT_CHECK_CUDA(cudaMemcpy2DAsync(dev_rows + (size_t)j * row_bytes, (size_t)n_rows * row_bytes,
+                                     host_frames + (size_t)host_rows[j] * row_bytes, (size_t)period * row_bytes,
+                                     row_bytes, periods, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  }
   return VBT_OK;
 }

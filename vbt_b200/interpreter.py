@@ -104,6 +104,15 @@ class Detector:
                                                 _lib.stream_ptr(stream)))
         return self.resized[:B]
 
+    def preprocess_rows(self, ingest, table, n, swap_rb=True, stream=None):
+        """K1 over a compacted row table produced by `ingest.RowSparseIngest.upload`."""
+        assert n <= self.max_batch and ingest.S == self.S
+        _lib.check(_lib.lib().vbt_preprocess_rows_u8(table.data_ptr(), n, ingest.H, ingest.W,
+                                                     ingest.rows_per_frame, ingest.row_map.data_ptr(),
+                                                     int(swap_rb), self.resized.data_ptr(), self.S,
+                                                     _lib.stream_ptr(stream)))
+        return self.resized[:n]
+
     def network(self, images, stream=None):
         """images: uint8 CUDA [B,S,S,3] RGB -> raw int8 class scores / box encodings."""
         B = images.shape[0]

@@ -65,11 +65,21 @@ class VideoPipeline:
         self.side = t.cuda.Stream()
         self.det_ready = [t.cuda.Event() for _ in range(S)]
         self.slot_free = [t.cuda.Event() for _ in range(S)]
-        self.input_consumed = None     # event: the last batch's frames have been read (K1 done)
+        self.input_consumed = None     # event: the last batch's frames have been read (K1 / DMA done)
+        self.ingest = None             # ingest.RowSparseIngest for host frames (use_row_sparse_ingest)
         self.batches = 0
         self.last_slot = 0
         self.frames_done = 0
         self.stage_events = None      # bench.py: list of per-step event tuples when profiling
+
+    def use_row_sparse_ingest(self, H, W):
+        """Host frames of this size are sent row-sparse (only the rows the resize reads)."""
+        from .ingest import RowSparseIngest
+        if (W * 3) % 16 or (H * W * 3) % 16:       # K1's bulk-copy path needs 16-byte rows
+            self.ingest = None
+        else:
+            self.ingest = RowSparseIngest(self.F, H, W, self.det.S)
+        return self.ingest
 
     def _mark(self, marks, stream=None):
         if marks is not None:
@@ -113,14 +123,26 @@ class VideoPipeline:
         arrived = t.cuda.Event()
         arrived.record()
         ds.wait_event(arrived)
-        if frames.is_cuda:              # pinned host frames are read in place by K1 (zero copy)
+        table = None
+        if frames.is_cuda:
             frames.record_stream(ds)
+        elif self.ingest is not None and tuple(frames.shape[1:3]) == (self.ingest.H, self.ingest.W):
+            # host frames: DMA only the rows K1 touches (ingest.py), on the ingest stream
+            table, n, tslot, ready = self.ingest.upload(frames)
+            self.input_consumed = ready            # the host buffer is free once the DMA is done
+            ds.wait_event(ready)
+        # else: pinned host frames are read in place by K1 (zero copy)
         frame_numbers.record_stream(ds)
         with t.cuda.stream(ds):
             self._mark(marks)
-            images = det.preprocess(frames, swap_rb)
-            self.input_consumed = t.cuda.Event()
-            self.input_consumed.record(ds)
+            if table is not None:
+                images = det.preprocess_rows(self.ingest, table, n, swap_rb)
+                self.ingest.free[tslot] = t.cuda.Event()
+                self.ingest.free[tslot].record(ds)
+            else:
+                images = det.preprocess(frames, swap_rb)
+                self.input_consumed = t.cuda.Event()
+                self.input_consumed.record(ds)
             self._mark(marks)
             det.network(images)
             self._mark(marks)

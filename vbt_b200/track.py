@@ -61,11 +61,17 @@ def track(src, interpreter, detection_treshold, display_image_height=720, video_
             copied[k].synchronize()                 # the H2D copy that last read this buffer is done
         for i, f in enumerate(staged):
             pinned[k][i].copy_(torch.from_numpy(f))
-        dev = pinned[k][:n].to('cuda', non_blocking=True)
-        copied[k] = torch.cuda.Event()
-        copied[k].record()
+        if flushes == 1:
+            pipe.use_row_sparse_ingest(h, w)           # host frames: send only the rows K1 reads
         nums = torch.as_tensor(np.asarray(numbers, dtype=np.int32), device='cuda')
-        pipe.process(dev, nums, swap_rb=True)          # cv2 frames are BGR (track.py:171)
+        if pipe.ingest is not None:
+            pipe.process(pinned[k][:n], nums, swap_rb=True)    # cv2 frames are BGR (track.py:171)
+            copied[k] = pipe.input_consumed
+        else:
+            dev = pinned[k][:n].to('cuda', non_blocking=True)
+            copied[k] = torch.cuda.Event()
+            copied[k].record()
+            pipe.process(dev, nums, swap_rb=True)
         staged.clear()
         numbers.clear()
 
