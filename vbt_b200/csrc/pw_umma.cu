@@ -26,6 +26,8 @@ namespace {
 using vbt::OpRecord;
 
 constexpr int TILE_M = 128;
+constexpr int NT = 256;             // threads per CTA: two warps per TMEM lane quarter, each takes
+                                   // half of the chunk's columns in the epilogue
 constexpr int KCH_STAGE = 16;      // 16-byte K chunks per K iteration (256 bytes of K)
 
 struct PwUmmaArgs {
@@ -91,7 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 template <bool HAS_RES>
-__global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
+__global__ void __launch_bounds__(NT) pw_umma_kernel(PwUmmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
   __shared__ uint32_t tmem_base_s;
@@ -124,13 +126,13 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)));
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
-  for (int i = tid; i < nc; i += 128) { sBias[i] = a.bias[n0 + i]; sMult[i] = a.mult[n0 + i]; }
+  for (int i = tid; i < nc; i += NT) { sBias[i] = a.bias[n0 + i]; sMult[i] = a.mult[n0 + i]; }
   vbt::pdl_wait();                 // everything above touched only model constants and this CTA's own state
   vbt::pdl_launch_dependents();
   if (HAS_RES) {                                    // residual tile, row-padded like the output
     const int cpr = nc >> 4;
     const uint32_t inv_c = (nc == a.nc) ? a.inv_cpr : (65536u + cpr - 1) / cpr;
-    for (int i = tid; i < TILE_M * cpr; i += 128) {
+    for (int i = tid; i < TILE_M * cpr; i += NT) {
       const int r = div_small(i, inv_c), j = i - r * cpr;
       const long long m = m0 + r;
       const bool ok = m < a.M;
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
     // row (g*8+rr), chunk kc.  Consecutive lanes walk rr fastest: 8 rows x 16 B = one
     // conflict-free 128-byte shared line; 4 chunks of the same row per warp coalesce.
     const int a_items = (TILE_M / 8) * kpad * 8;
-    for (int it = tid; it < a_items; it += 128) {
+    for (int it = tid; it < a_items; it += NT) {
       const int rr = it & 7, q = it >> 3;
       const int g = div_small(q, inv), kc = q - g * kpad;
       const long long m = m0 + g * 8 + rr;
@@ -165,7 +167,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
       cp_async16(dst, a.in + (ok ? m : 0) * a.cin_p + (size_t)(kc0 + (ok ? kc : 0)) * 16, ok);
     }
     const int b_items = (nc / 8) * kpad * 8;
-    for (int it = tid; it < b_items; it += 128) {
+    for (int it = tid; it < b_items; it += NT) {
       const int rr = it & 7, q = it >> 3;
       const int g = div_small(q, inv), kc = q - g * kpad;
       const int n = n0 + g * 8 + rr;
@@ -192,12 +194,16 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   }
   asm volatile("tcgen05.fence::after_thread_sync;\n");
 
-  // ---- epilogue: thread t owns row t of the tile = TMEM lane t ---------------------------
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
-  unsigned char* orow = sOut + (size_t)tid * a.out_stride;
-  const unsigned char* rrow = sRes + (size_t)tid * a.out_stride;
+  // ---- epilogue: warp w reads TMEM lanes 32*(w%4).. (rows of the tile); warps 0-3 take the
+  //      lower half of the chunk's columns, warps 4-7 the upper half ------------------------
+  const int row = ((warp & 3) << 5) | (tid & 31);
+  const int split = ((nc >> 4) + 1) / 2 * 16;
+  const int c_begin = (warp >> 2) ? split : 0, c_end = (warp >> 2) ? nc : split;
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  unsigned char* orow = sOut + (size_t)row * a.out_stride;
+  const unsigned char* rrow = sRes + (size_t)row * a.out_stride;
   const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
-  for (int c0 = 0; c0 < nc; c0 += 16) {
+  for (int c0 = c_begin; c0 < c_end; c0 += 16) {
     uint32_t v[16];
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
@@ -236,7 +242,7 @@ __global__ void __launch_bounds__(128) pw_umma_kernel(PwUmmaArgs a) {
   {
     const int cpr = nc >> 4;
     const uint32_t inv_c = (nc == a.nc) ? a.inv_cpr : (65536u + cpr - 1) / cpr;
-    for (int i = tid; i < TILE_M * cpr; i += 128) {
+    for (int i = tid; i < TILE_M * cpr; i += NT) {
       const int r = div_small(i, inv_c), j = i - r * cpr;
       const long long m = m0 + r;
       if (m < a.M)
@@ -312,8 +318,8 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   }
   if (smem > 200 * 1024) return VBT_OK;
   dim3 grid((unsigned)((a.M + TILE_M - 1) / TILE_M), (unsigned)((op.cout_p + a.nc - 1) / a.nc));
-  if (has_res) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<true>, grid, dim3(128), smem, st, a));
-  else VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false>, grid, dim3(128), smem, st, a));
+  if (has_res) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<true>, grid, dim3(NT), smem, st, a));
+  else VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false>, grid, dim3(NT), smem, st, a));
   *taken = true;
   return VBT_OK;
 }
