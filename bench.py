@@ -119,7 +119,7 @@ def op_algorithmic(g, op, E):
         if op.residual >= 0:
             r = g.tensors[op.residual]
             in_el += r.h * r.w * r.c
-        return 'pw', in_el + out_el + w, 2 * ins[0].h * ins[0].w * ins[0].c * cout
+        return ('pw' if op.out_kind == 0 else 'pw_head_out'), in_el + out_el + w, 2 * ins[0].h * ins[0].w * ins[0].c * cout
     if op.type == E.OP_DW:
         t = g.tensors[op.out]
         return f'dw{op.k}', in_el + out_el + t.c * (op.k * op.k + 8), 2 * t.h * t.w * t.c * op.k * op.k

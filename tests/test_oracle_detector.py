@@ -88,3 +88,19 @@ def test_resize_identity_known_values_and_truncation():
     assert lo[0] == 1 and hi[0] == 2 and abs(lerp[0] - 0.1875) < 1e-6     # (0.5 * 3.375) - 0.5 = 1.1875
     flipped = OR.resize_bilinear_u8(img, 8, swap_rb=True)
     assert np.array_equal(flipped, OR.resize_bilinear_u8(img[..., ::-1], 8))
+
+
+def test_network_oracle_float32_fast_path_is_exact():
+    """oracle/effdet.py evaluates integer convolutions in float32 where partial sums stay below
+    2^24 and in float64 elsewhere; forcing float64 everywhere must not change a single value."""
+    from oracle import effdet as OE
+    from vbt_b200.synth import synthetic_model_inputs
+    g = E.build_synthetic('lite0')
+    x = synthetic_model_inputs(1, g.S, seed=3)
+    cls, box, _ = OE.run(g, x)
+    OE.FORCE_F64 = True
+    try:
+        cls64, box64, _ = OE.run(g, x)
+    finally:
+        OE.FORCE_F64 = False
+    assert np.array_equal(cls, cls64) and np.array_equal(box, box64)
