@@ -76,6 +76,9 @@ void vbt_model_destroy(vbt_model* m);
 /* info[0]=input size S, [1]=anchors N, [2]=workspace bytes per frame, [3]=ops,
  * [4]=classes, [5]=kernels launched per vbt_detect call, [6]=Np (N rounded up to 16) */
 int vbt_model_info(const vbt_model* m, long long info[8]);
+/* launch plan: group_len i32 [ops] on the host; group_len[i] = number of consecutive ops the
+ * kernel launched at op i covers (fused [ADD ->] DW3x3 -> PW groups), 0 for ops inside a group */
+int vbt_model_plan(const vbt_model* m, int32_t* host_group_len);
 /* in: u8 [B,S,S,3] RGB; out_cls: i8 [B,Np] post-LOGISTIC scores (scale 1/256, zp -128);
  * out_box: i8 [B,Np,4] (ty,tx,th,tw) with the model's box quantisation; Np = info[6] =
  * N rounded up to 16 (row stride; the pad entries are never read).

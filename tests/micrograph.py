@@ -24,7 +24,7 @@ def _empty_graph(h, w, c, zp):
 
 
 def _conv_q(rng, op, g, zp_in, zp_out, act, fan_in):
-    cout = g.tensors[op.out].c
+    cout = g.out_channels(op)
     q = op.q
     q['zp_in'] = [zp_in]
     q['zp_out'] = q['conv_zp_out'] = zp_out
@@ -70,6 +70,68 @@ def dw_graph(h, w, c, k, stride, act=True, seed=0, zp_in=-9, zp_out=-20):
     return g
 
 
+def _set_dw(rng, g, op, zp_in, zp_out, act):
+    c = g.tensors[op.out].c
+    op.q['w'] = rng.integers(-127, 128, (c, op.k, op.k)).astype(np.int8)
+    _conv_q(rng, op, g, zp_in, zp_out, act, op.k * op.k)
+    g.tensors[op.out].zp = zp_out
+
+
+def _set_pw(rng, g, op, cin, cout, zp_in, zp_out, act):
+    op.q['w'] = rng.integers(-127, 128, (cout, cin)).astype(np.int8)
+    _conv_q(rng, op, g, zp_in, zp_out, act, cin)
+    if op.out >= 0:
+        g.tensors[op.out].zp = zp_out
+
+
+def head_graph(h, w, c, cout, act=True, seed=0, out_kind=0):
+    """input -> DW3x3 s1 -> PW(c->cout): one stage of the class / box nets, the pair
+    csrc/node_umma.cu runs as one kernel.  out_kind 1 / 2: packed raw head outputs."""
+    rng = np.random.default_rng(seed)
+    g = _empty_graph(h, w, c, -9)
+    if out_kind:
+        g.level_sizes, g.n_anchors = [(h, w)], h * w * 9
+    d = g._dw(g.input, 3, 1, False, 'dw0')
+    _set_dw(rng, g, g.ops[-1], -9, -20, False)
+    g._pw(d, cout, act, 'pw0', out_kind=out_kind)
+    _set_pw(rng, g, g.ops[-1], c, cout, -20, 11, act)
+    if out_kind == 1:
+        qs = np.arange(-128, 128)
+        g.ops[-1].q['lut'] = np.clip(np.rint(256.0 / (1.0 + np.exp(-(qs - 11) * 0.06))) - 128,
+                                     -128, 127).astype(np.int8)
+    return g
+
+
+def node_graph(h, w, c, n_in=3, seed=0, odd=False):
+    """A BiFPN node on a pyramid built from the input: input [2h(-1), 2w(-1)] -> DW s2 -> p1
+    [h, w] -> DW s2 -> p2; then ADD(max-pooled input, p1, up-sampled p2) -> ReLU6 -> DW3x3 ->
+    PW(c->c), the triple csrc/node_umma.cu runs as one kernel.  n_in = 2 drops the max-pooled
+    input.  odd: the input is (2h-1, 2w-1), the 5 -> 3 / 7 -> 4 pooling case."""
+    rng = np.random.default_rng(seed)
+    g = _empty_graph(2 * h - (1 if odd else 0), 2 * w - (1 if odd else 0), c, 4)
+    g.S = g.tensors[g.input].h
+    p1 = g._dw(g.input, 3, 2, False, 'p1')
+    _set_dw(rng, g, g.ops[-1], 4, -13, False)
+    assert (g.tensors[p1].h, g.tensors[p1].w) == (h, w)
+    p2 = g._dw(p1, 3, 2, False, 'p2')
+    _set_dw(rng, g, g.ops[-1], -13, 21, False)
+    xs = [g.input, p1, p2] if n_in == 3 else [p1, p2]
+    f = g._fuse(xs, (h, w), 'n.sum')
+    op = g.ops[-1]
+    zp_out = -128
+    op.q['zp_in'] = [g.tensors[x].zp for x in xs]
+    op.q['zp_out'] = zp_out
+    op.q['act_lo'], op.q['act_hi'] = zp_out, 95
+    op.q['add_mult'] = [int(m * (1 << 20)) for m in (0.43, 0.71, 0.52)][3 - n_in:]
+    op.q['add_shift'] = 20
+    g.tensors[f].zp = zp_out
+    d = g._dw(f, 3, 1, False, 'n.dw')
+    _set_dw(rng, g, g.ops[-1], zp_out, -6, False)
+    g._pw(d, c, False, 'n.pw')
+    _set_pw(rng, g, g.ops[-1], c, c, -6, 17, False)
+    return g
+
+
 def random_input(g, B, seed=1):
     """(logical int8 [B,h,w,c], padded int8 [B,h,w,c_p] with the zero point in the pad)."""
     t = g.tensors[g.input]
@@ -91,7 +153,20 @@ def run_gpu(g, xp):
     torch.cuda.synchronize()
     ws = det.workspace.cpu().numpy().view(np.int8)
     out = {}
-    for op in g.ops:
+    plan = det.plan()
+    run_gpu.last_plan = plan
+    for i, op in enumerate(g.ops):
+        # tensors inside a fused run never reach the workspace: only a launch's last op does
+        j = i
+        while plan[j] == 0:
+            j -= 1
+        if i != j + plan[j] - 1:
+            continue
+        if op.out < 0:
+            n = g.n_anchors
+            raw = (det.raw_cls if op.out_kind == 1 else det.raw_box)[:B].cpu().numpy()
+            out[-op.out_kind] = raw[:, :n] if op.out_kind == 1 else raw[:, :n, :]
+            continue
         t = g.tensors[op.out]
         off = B * t.ws_offset
         full = ws[off:off + B * t.h * t.w * t.c_p].reshape(B, t.h, t.w, t.c_p)

@@ -16,6 +16,8 @@ def check(g, B, seed=1):
     _, _, want = OE.run(g, x, keep=True)
     got = MG.run_gpu(g, xp)
     for op in g.ops:
+        if op.out not in got:
+            continue                               # inside a fused run
         t = g.tensors[op.out]
         vals, pad = got[op.out]
         assert np.array_equal(vals.astype(np.int16), want[op.out]), f'{op.name}: values differ'
@@ -75,3 +77,45 @@ def test_depthwise_both_implementations(impl):
     r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, VBT_DW_IMPL=impl),
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+# ---- fused [ADD ->] DW3x3 -> PW kernel (csrc/node_umma.cu) ---------------------------------
+
+@pytest.mark.parametrize('h,w,c,cout,B', [
+    (3, 3, 64, 64, 5), (5, 5, 64, 64, 3), (10, 10, 64, 64, 2), (20, 20, 64, 64, 2), (40, 40, 64, 64, 2),
+    (6, 6, 88, 88, 3), (12, 12, 88, 88, 2), (24, 24, 88, 88, 2), (48, 48, 88, 88, 1),
+    (4, 4, 112, 112, 3), (7, 7, 112, 112, 2), (28, 28, 112, 112, 1), (56, 56, 112, 112, 1),
+    (9, 13, 16, 16, 2), (11, 6, 128, 128, 2), (17, 19, 40, 24, 1),
+])
+def test_fused_head_stage(h, w, c, cout, B):
+    g = MG.head_graph(h, w, c, cout, act=True, seed=h * 100 + c)
+    check(g, B)
+    assert list(MG.run_gpu.last_plan) == [2, 0], 'the DW -> PW pair must run as one kernel'
+
+
+@pytest.mark.parametrize('h,w,c,kind', [(5, 5, 64, 1), (20, 20, 64, 2), (12, 12, 88, 1), (24, 24, 88, 2),
+                                        (48, 48, 88, 2), (7, 7, 112, 2), (56, 56, 112, 1)])
+def test_fused_head_output(h, w, c, kind):
+    """Packed 9 / 36-channel raw outputs (+ LOGISTIC LUT on the class head) from the fused kernel."""
+    B = 2
+    g = MG.head_graph(h, w, c, 9 if kind == 1 else 36, act=False, seed=h + c, out_kind=kind)
+    x, xp = MG.random_input(g, B, 3)
+    cls, box, _ = OE.run(g, x)
+    got = MG.run_gpu(g, xp)
+    assert list(MG.run_gpu.last_plan) == [2, 0]
+    if kind == 1:
+        assert np.array_equal(got[-1], cls)
+    else:
+        assert np.array_equal(got[-2], box)
+
+
+@pytest.mark.parametrize('h,w,c,n_in,odd,B', [
+    (3, 3, 64, 3, True, 4), (5, 5, 64, 3, False, 3), (10, 10, 64, 3, False, 2), (20, 20, 64, 3, False, 2),
+    (40, 40, 64, 2, False, 1), (6, 6, 88, 3, False, 2), (12, 12, 88, 3, False, 2), (24, 24, 88, 3, False, 2),
+    (48, 48, 88, 2, False, 1), (4, 4, 112, 3, True, 2), (14, 14, 112, 3, False, 2), (28, 28, 112, 3, False, 1),
+    (56, 56, 112, 2, False, 1), (9, 7, 32, 3, True, 2),
+])
+def test_fused_bifpn_node(h, w, c, n_in, odd, B):
+    g = MG.node_graph(h, w, c, n_in=n_in, seed=h * 10 + c, odd=odd)
+    check(g, B)
+    assert list(MG.run_gpu.last_plan)[-3:] == [3, 0, 0], 'ADD -> DW -> PW must run as one kernel'

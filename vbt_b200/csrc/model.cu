@@ -112,6 +112,55 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
     VBT_CHECK_CUDA(cudaStreamCreateWithFlags(&m->branch_stream[k], cudaStreamNonBlocking));
     VBT_CHECK_CUDA(cudaEventCreateWithFlags(&m->join_event[k], cudaEventDisableTiming));
   }
+  // ---- launch plan: which op runs of the program are served by one fused kernel -----------
+  {
+    const int n = (int)m->ops.size();
+    std::vector<int> readers(hdr.n_tensors, 0);
+    for (const OpRecord& op : m->ops)
+      for (int i = 0; i < op.n_in; ++i)
+        if (op.in[i] >= 0) readers[op.in[i]] += 1;
+    static const int max_hw = [] { const char* e = getenv("VBT_FUSE_HW"); return e ? atoi(e) : 64; }();
+    auto dw_ok = [&](const OpRecord& d) {
+      return d.type == OP_DW && d.k == 3 && d.stride == 1 && d.cout_p <= 128 && d.lut_off >= 0 &&
+             d.h_in <= max_hw && d.w_in <= max_hw && d.out >= 0 && readers[d.out] == 1;
+    };
+    auto pw_ok = [&](const OpRecord& p, const OpRecord& d) {
+      return p.type == OP_PW && p.n_in == 1 && p.in[0] == d.out && p.branch == d.branch && p.cout_p <= 128 &&
+             p.cout_p % 16 == 0 && p.cin_p == d.cout_p;
+    };
+    // one kernel's CTAs write the run's output while others still read its inputs: the two
+    // must not share workspace memory (effdet.plan_workspace keeps them apart)
+    auto disjoint = [&](const OpRecord& first, const OpRecord& last) {
+      if (last.out < 0) return true;
+      const TensorRecord& to = m->tensors[last.out];
+      const int64_t o0 = to.ws_offset, o1 = o0 + (int64_t)to.h * to.w * to.c_p;
+      for (int i = 0; i < first.n_in; ++i) {
+        if (first.in[i] < 0) continue;
+        const TensorRecord& ti = m->tensors[first.in[i]];
+        if (ti.ws_offset < 0) continue;               // the model input: caller's buffer
+        const int64_t i0 = ti.ws_offset, i1 = i0 + (int64_t)ti.h * ti.w * ti.c_p;
+        if (o0 < i1 && i0 < o1) return false;
+      }
+      return true;
+    };
+    m->fuse.assign(n, 1);
+    for (int i = 0; i < n;) {
+      const OpRecord& o = m->ops[i];
+      if (max_hw > 0 && o.type == OP_ADD && i + 2 < n && o.out >= 0 && readers[o.out] == 1 &&
+          m->ops[i + 1].in[0] == o.out && m->ops[i + 1].branch == o.branch && dw_ok(m->ops[i + 1]) &&
+          pw_ok(m->ops[i + 2], m->ops[i + 1]) && disjoint(o, m->ops[i + 2])) {
+        m->fuse[i] = 3; m->fuse[i + 1] = m->fuse[i + 2] = 0;
+        i += 3;
+      } else if (max_hw > 0 && i + 1 < n && dw_ok(o) && pw_ok(m->ops[i + 1], o) && disjoint(o, m->ops[i + 1])) {
+        m->fuse[i] = 2; m->fuse[i + 1] = 0;
+        i += 2;
+      } else {
+        i += 1;
+      }
+    }
+    m->kernels_per_detect = 0;
+    for (int f : m->fuse) m->kernels_per_detect += f > 0;
+  }
   // a branch may start as soon as the trunk op that writes its input tensor is enqueued
   for (int k = 0; k < m->n_branches; ++k) {
     VBT_CHECK_CUDA(cudaEventCreateWithFlags(&m->fork_event[k], cudaEventDisableTiming));
@@ -153,6 +202,12 @@ int vbt_model_info(const vbt_model* m, long long info[8]) {
   info[5] = m->kernels_per_detect;
   info[6] = m->hdr.n_anchors_pad;
   info[7] = 0;
+  return VBT_OK;
+}
+
+int vbt_model_plan(const vbt_model* m, int32_t* host_group_len) {
+  VBT_REQUIRE(m && host_group_len, "vbt_model_plan: null pointer");
+  for (size_t i = 0; i < m->ops.size(); ++i) host_group_len[i] = m->fuse[i];
   return VBT_OK;
 }
 

@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 7;
+constexpr int kBlobVersion = 8;
 
 struct BlobHeader {
   uint32_t magic;
@@ -101,6 +101,9 @@ struct vbt_model {
   cudaEvent_t fork_event[kMaxBranches] = {}, join_event[kMaxBranches] = {};
   int fork_after[kMaxBranches] = {};   // index of the trunk op that produces branch k's input
   int n_branches = 0;      // highest branch id used by the program
+  // launch plan: fuse[i] = number of consecutive ops the launch starting at op i covers
+  // ([ADD ->] DW3x3 -> PW on small maps run as one node_umma kernel), 0 for ops inside a group
+  std::vector<int> fuse;
   // CUDA graphs of the layer program, one per (buffers, batch) a caller has used twice
   struct GraphKey {
     const void *in, *ws, *cls, *box; int B;
@@ -109,6 +112,8 @@ struct vbt_model {
     }
   };
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int> graph_kernels;   // kernel nodes of each captured graph
+  int kernels_last_run = 0;                // kernels the last run_ops enqueued (fused runs count once)
   std::set<GraphKey> graph_seen;
   // optional per-op timing (bench.py): a ring of event sets, harvested lazily
   bool profile = false;

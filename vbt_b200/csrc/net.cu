@@ -24,6 +24,9 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
                    int8_t* out, long long out_batch_stride, int B, cudaStream_t st, bool* taken);
 int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int8_t* out, int B,
                    cudaStream_t st, bool* taken);
+int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw, const OpRecord& pw,
+                     const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
+                     cudaStream_t st, bool* taken);
 }
 
 namespace {
@@ -490,18 +493,41 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
   };
   auto data = [&](int64_t off) { return off < 0 ? nullptr : m->dev_data + off; };
   int launched = 0;
+  m->kernels_last_run = 0;
   // Branch k > 0 (a head chain) runs on its own stream: forked once the trunk is enqueued,
   // joined at the end.  Under stream capture this becomes parallel branches of the graph.
   const bool fork = !prof && m->n_branches > 0;
   bool started[vbt_model::kMaxBranches] = {};
   if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], main_st));
-  for (const OpRecord& op : m->ops) {
+  const int n_ops = (int)m->ops.size();
+  for (int oi = 0; oi < n_ops; ++oi) {
+    const OpRecord& op = m->ops[oi];
     cudaStream_t st = main_st;
     if (fork && op.branch > 0) {
       const int k = op.branch - 1;
       if (!started[k]) { VBT_CHECK_CUDA(cudaStreamWaitEvent(m->branch_stream[k], m->fork_event[k], 0)); started[k] = true; }
       st = m->branch_stream[k];
     }
+    // fused [ADD ->] DW3x3 -> PW group: one kernel; falls through to the single ops if declined
+    int covered = 1;
+    if (m->fuse[oi] > 1) {
+      const int glen = m->fuse[oi];
+      const OpRecord* add = glen == 3 ? &op : nullptr;
+      const OpRecord& dwop = m->ops[oi + glen - 2];
+      const OpRecord& pwop = m->ops[oi + glen - 1];
+      const int8_t* ins[3] = {nullptr, nullptr, nullptr};
+      if (add) for (int i = 0; i < add->n_in; ++i) ins[i] = tensor_ptr(add->in[i]);
+      else ins[0] = tensor_ptr(dwop.in[0]);
+      int8_t* out;
+      long long obs;
+      if (pwop.out_kind == 0) { out = tensor_ptr(pwop.out); obs = (long long)pwop.h_out * pwop.w_out * pwop.cout_p; }
+      else if (pwop.out_kind == 1) { out = dev_out_cls; obs = Np * m->hdr.n_classes; }
+      else { out = dev_out_box; obs = Np * 4; }
+      bool node_taken = false;
+      if (int rc = launch_node_umma(m, add, dwop, pwop, ins, out, obs, B, st, &node_taken)) return rc;
+      if (node_taken) covered = glen;
+    }
+    if (covered == 1) {
     switch (op.type) {
       case OP_STEM: {
         StemArgs a;
@@ -586,12 +612,17 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
       default:
         VBT_REQUIRE(false, "vbt_detect: unknown op type %d", op.type);
     }
-    ++launched;
+    }
     VBT_CHECK_CUDA(cudaPeekAtLastError());
-    if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], main_st));
-    if (fork && op.branch == 0)
-      for (int k = 0; k < m->n_branches; ++k)
-        if (m->fork_after[k] == launched - 1) VBT_CHECK_CUDA(cudaEventRecord(m->fork_event[k], main_st));
+    ++m->kernels_last_run;
+    for (int c = 0; c < covered; ++c) {              // a group's time lands on its first op
+      ++launched;
+      if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[launched], main_st));
+      if (fork && op.branch == 0)
+        for (int k = 0; k < m->n_branches; ++k)
+          if (m->fork_after[k] == launched - 1) VBT_CHECK_CUDA(cudaEventRecord(m->fork_event[k], main_st));
+    }
+    oi += covered - 1;
   }
   for (int k = 0; k < vbt_model::kMaxBranches; ++k) {
     if (!started[k]) continue;
@@ -622,7 +653,7 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
   static const bool use_graph = [] { const char* e = getenv("VBT_GRAPH"); return !(e && e[0] == '0'); }();
   if (!use_graph || prof || st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread) {
     if (int rc = run_ops(m, dev_in, B, dev_workspace, dev_out_cls, dev_out_box, st, prof)) return rc;
-    vbt::count_launches(n_ops);
+    vbt::count_launches(m->kernels_last_run);
     return VBT_OK;
   }
   const vbt_model::GraphKey key{dev_in, dev_workspace, dev_out_cls, dev_out_box, B};
@@ -634,7 +665,7 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
       // cudaFuncSetAttribute outside of a capture); capture on the next call
       m->graph_seen.insert(key);
       if (int rc = run_ops(m, dev_in, B, dev_workspace, dev_out_cls, dev_out_box, st, nullptr)) return rc;
-      vbt::count_launches(n_ops);
+      vbt::count_launches(m->kernels_last_run);
       return VBT_OK;
     }
     cudaGraph_t graph = nullptr;
@@ -647,8 +678,9 @@ extern "C" int vbt_detect(vbt_model* m, const uint8_t* dev_in, int B, void* dev_
     VBT_CHECK_CUDA(cudaGraphInstantiate(&exec, graph, 0));
     cudaGraphDestroy(graph);
     it = m->graphs.emplace(key, exec).first;
+    m->graph_kernels[key] = m->kernels_last_run;
   }
   VBT_CHECK_CUDA(cudaGraphLaunch(it->second, st));
-  vbt::count_launches(n_ops);
+  vbt::count_launches(m->graph_kernels[key]);
   return VBT_OK;
 }

@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 7
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 8
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -43,6 +43,7 @@ _STAGES = [(3, 1, 16, 1, 1), (3, 2, 24, 6, 2), (5, 2, 40, 6, 2), (3, 3, 80, 6, 2
            (5, 3, 112, 6, 1), (5, 4, 192, 6, 2), (3, 1, 320, 6, 1)]
 NUM_SCALES, ASPECTS, ANCHOR_SCALE = 3, (1.0, 2.0, 0.5), 3.0
 NUM_CLASSES = 1
+FUSE_MAX_HW = 64       # largest map side the fused node kernel takes (csrc/model.cu)
 
 
 def pad16(c):
@@ -458,6 +459,41 @@ def quantize(g: Graph, calib_frames):
     return g
 
 
+def fused_run_end(g):
+    """run_end[i] = index of the last op of the [ADD ->] DW3x3 s1 -> PW run op i may be executed
+    in as one kernel (vbt_model_create's launch plan, csrc/model.cu), i itself otherwise.  A
+    superset of what the library fuses is fine: it only delays memory reuse."""
+    n = len(g.ops)
+    readers = {}
+    for op in g.ops:
+        for t in op.inputs + ([op.residual] if op.residual >= 0 else []):
+            readers[t] = readers.get(t, 0) + 1
+    end = list(range(n))
+
+    def dw_pw(i):
+        if i + 1 >= n:
+            return False
+        d, p = g.ops[i], g.ops[i + 1]
+        t = g.tensors[d.out]
+        return (d.type == OP_DW and d.k == 3 and d.stride == 1 and readers.get(d.out, 0) == 1 and
+                t.c_p <= 128 and max(t.h, t.w) <= FUSE_MAX_HW and pad16(g.out_channels(p)) <= 128 and
+                p.type == OP_PW and p.inputs == [d.out] and p.residual < 0 and p.branch == d.branch)
+
+    i = 0
+    while i < n:
+        o = g.ops[i]
+        if o.type == OP_ADD and readers.get(o.out, 0) == 1 and dw_pw(i + 1) and \
+                g.ops[i + 1].inputs == [o.out] and g.ops[i + 1].branch == o.branch:
+            end[i] = end[i + 1] = end[i + 2] = i + 2
+            i += 3
+        elif dw_pw(i):
+            end[i] = end[i + 1] = i + 1
+            i += 2
+        else:
+            i += 1
+    return end
+
+
 def plan_workspace(g: Graph):
     """First-fit allocation of per-frame activation offsets with liveness reuse.
 
@@ -500,9 +536,19 @@ def plan_workspace(g: Graph):
                 merged.append((o2, s2))
         free[:] = merged
 
+    # The library runs [ADD ->] DW3x3 -> PW runs as ONE kernel (csrc/node_umma.cu) whose CTAs
+    # write the last op's output while other CTAs still read the first op's inputs: tensors
+    # read inside such a run are recycled only after the run's last op has its output placed.
+    run_end = fused_run_end(g)
     owner = {}
+    pending = []                           # (op index after which the tensor is free, tensor id)
     g.tensors[g.input].ws_offset = -1      # the input lives in the caller's buffer
     for i, op in enumerate(g.ops):
+        for item in [p for p in pending if p[0] < i]:
+            pending.remove(item)
+            tid = item[1]
+            bfree, bsizes = pools[owner[tid]]
+            release(bfree, g.tensors[tid].ws_offset, bsizes.pop(tid))
         free, sizes = pools.setdefault(op.branch, ([], {}))
         if op.out >= 0:
             t = g.tensors[op.out]
@@ -515,8 +561,7 @@ def plan_workspace(g: Graph):
             if b == 0 and tid in keep:
                 continue                   # read by a concurrent branch: stays until the end
             if b == op.branch:
-                bfree, bsizes = pools[b]
-                release(bfree, g.tensors[tid].ws_offset, bsizes.pop(tid))
+                pending.append((run_end[i], tid))
     g.ws_bytes_per_frame = top
     return top
 
@@ -588,7 +633,7 @@ def pack_blob(g: Graph):
         ins = [g.tensors[i] for i in op.inputs]
         tout = g.tensors[op.out] if op.out >= 0 else None
         cout = g.out_channels(op)
-        cout_p = tout.c_p if tout is not None else cout
+        cout_p = tout.c_p if tout is not None else pad16(cout)    # head outputs: padded rows are zero
         r = dict(type=op.type, out=op.out if op.out >= 0 else -1, n_in=len(op.inputs), k=op.k,
                  stride=op.stride, cin=ins[0].c, cout=cout, cin_p=ins[0].c_p, cout_p=cout_p,
                  h_in=ins[0].h, w_in=ins[0].w,

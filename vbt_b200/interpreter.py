@@ -83,6 +83,12 @@ class Detector:
     def profile(self, enable=True):
         _lib.check(_lib.lib().vbt_model_profile(self.handle, int(enable)))
 
+    def plan(self):
+        """int32 [n_ops]: ops covered by the launch that starts at each op (0 = inside a group)."""
+        g = np.ones(max(self.n_ops, 1), dtype=np.int32)
+        _lib.check(_lib.lib().vbt_model_plan(self.handle, _lib.ptr(g)))
+        return g[:self.n_ops]
+
     def op_times(self):
         """(ms per op accumulated [n_ops], number of vbt_detect calls covered)."""
         ms = np.zeros(max(self.n_ops, 1), dtype=np.float64)
