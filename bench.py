@@ -38,6 +38,8 @@ def parse():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--variant', default='lite0')
+    ap.add_argument('--head-dtype', default='int8', choices=['int8', 'bf16'],
+                    help='tensor-core data type of the class / box nets (BASELINE configs[3])')
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--clip-frames', type=int, default=CLIP_FRAMES)
     ap.add_argument('--cpu-sample', type=int, default=12, help='frames timed for cpu_baseline')
@@ -140,7 +142,7 @@ def run_reference(args, rank):
     from vbt_b200 import effdet
     from vbt_b200.synth import plate_trajectory
     torch.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1
-    g = effdet.build_synthetic(args.variant)
+    g = effdet.build_synthetic(args.variant, head_dtype=args.head_dtype)
     per_step = max(1, min(4, 60 // max(args.steps, 1)))
     rng = np.random.default_rng(0)
     bg = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
@@ -215,7 +217,7 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     B = args.batch
-    g = effdet.build_synthetic(args.variant)
+    g = effdet.build_synthetic(args.variant, head_dtype=args.head_dtype)
     det = Detector(g, max_batch=B)
     pipe = VideoPipeline(det, FPS, 0.5, row_cap=1 << 17)
     # every rank owns one whole video (weak scaling: videos are the shard unit)
@@ -452,7 +454,7 @@ def main():
                 'workload': 'configs[1]: EfficientDet-Lite0 (synthetic int8 weights) full track.py '
                             'pipeline on one synthetic 1080p 30 fps 60 s clip per GPU, frame batch 64, '
                             'frame stride 1',
-                'variant': args.variant, 'batch': B, 'clip_frames': args.clip_frames,
+                'variant': args.variant, 'head_dtype': args.head_dtype, 'batch': B, 'clip_frames': args.clip_frames,
                 'frames_per_timed_region': frames_all, 'videos_finished': state['videos'],
                 'detections_per_frame': dets_per_frame, 'live_tracks': live_tracks,
                 'cache': 'inputs larger than L2: 398 MB of frames per step vs 126 MB L2, no flush needed',

@@ -163,3 +163,30 @@ def test_config4_videos_sharded_and_gathered():
     f = vids[1]['frames'].cpu().numpy()
     want = oracle_rows(g, f[1::2], 60.0, thr, numbers=list(range(2, 10, 2)))
     assert np.array_equal(t2[0], want)
+
+
+def test_config3_lite2_bf16_heads_equal_int8_heads():
+    """configs[3], "int8 vs bf16 heads": the class / box nets' pointwise convs on the bf16 tensor
+    path (tcgen05.mma.kind::f16, fp32 accumulate) must reproduce the int8 path's raw outputs bit
+    for bit at frame batch 256 -- and both are the oracle's on the frames it is run on."""
+    import torch
+    from vbt_b200 import effdet
+    from vbt_b200.interpreter import Detector
+    g8 = graph('lite2')
+    g16 = effdet.build_synthetic('lite2', head_dtype='bf16')
+    n = 256
+    frames = synthetic_frames(n, 135, 240, seed=10)
+    dev = torch.as_tensor(frames, device='cuda')
+    d8, d16 = Detector(g8, max_batch=n), Detector(g16, max_batch=n)
+    plan = d16.plan()
+    heads = [i for i, op in enumerate(g16.ops) if op.branch > 0]
+    assert all(plan[i] in (0, 2) for i in heads), 'every head stage must run in the fused kernel'
+    d8.network(d8.preprocess(dev, True))
+    d16.network(d16.preprocess(dev, True))
+    cls8, box8 = d8.raw_cls[:n, :g8.n_anchors].cpu().numpy(), d8.raw_box[:n, :g8.n_anchors].cpu().numpy()
+    cls16, box16 = d16.raw_cls[:n, :g8.n_anchors].cpu().numpy(), d16.raw_box[:n, :g8.n_anchors].cpu().numpy()
+    assert np.array_equal(cls8, cls16) and np.array_equal(box8, box16)
+    pick = [0, n - 1]
+    imgs = OR.preprocess_batch(frames[pick], g8.S, swap_rb=True)
+    want_cls, want_box, _ = OE.run(g16, imgs)
+    assert np.array_equal(cls16[pick], want_cls) and np.array_equal(box16[pick], want_box)

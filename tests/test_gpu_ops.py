@@ -119,3 +119,78 @@ def test_fused_bifpn_node(h, w, c, n_in, odd, B):
     g = MG.node_graph(h, w, c, n_in=n_in, seed=h * 10 + c, odd=odd)
     check(g, B)
     assert list(MG.run_gpu.last_plan)[-3:] == [3, 0, 0], 'ADD -> DW -> PW must run as one kernel'
+
+
+# ---- requantisation: packed 16-bit path vs the plain one, exact ties --------------------------
+
+@pytest.mark.parametrize('mult,fast', [(0.5, 1), (0.25, 1), (0.125, 1), (8.0, 0)])
+@pytest.mark.parametrize('zp_out', [11, -20, -128])
+def test_requant_ties_and_both_paths(mult, fast, zp_out):
+    """Power-of-two multipliers put acc * M exactly on .5 for every odd accumulator: the result
+    must go to the even integer BEFORE the zero point is added (odd and even zero points), on
+    the packed path (requant_fast = 1) and on the plain one (bound too large: requant_fast = 0)."""
+    from vbt_b200 import effdet as E
+    for g in (MG.pw_graph(9, 9, 16, 32, act=True, seed=5, zp_out=zp_out),
+              MG.dw_graph(9, 11, 32, 3, 1, act=True, seed=6, zp_out=zp_out),
+              MG.dw_graph(9, 11, 32, 5, 1, act=False, seed=7, zp_out=zp_out),
+              MG.head_graph(7, 7, 64, 64, act=True, seed=8)):
+        for op in g.ops:
+            n = op.q['mult'].shape[0]
+            op.q['mult'] = np.full(n, mult, np.float32)
+            op.q['w'] = np.clip(op.q['w'], -3, 3)               # small accumulators: many land in range
+            op.q['bias'] = (op.q['bias'] % 7).astype(np.int32)
+        E.pack_blob(g)
+        check(g, 2)
+
+
+# ---- persistent warp-specialised pointwise kernel (csrc/pw_persist.cu) -------------------------
+
+def test_pointwise_persistent_kernel():
+    """pw_persist.cu (opt-in: VBT_PW_PERSIST=1) takes large-M, K <= 256 layers; MIN_TILES=1 forces it for
+    every eligible shape here: M tails, one tile, many tiles per CTA (ring and accumulator phases
+    wrap several times), odd K chunk counts, two N chunks, residual epilogue.  The env var is read
+    once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_ops as T; '
+            'import micrograph as MG\n'
+            'for (h, w, cin, cout, B, act) in [(8, 16, 16, 16, 1, False), (5, 7, 16, 96, 3, True), (9, 9, 24, 144, 2, True), '
+            '(9, 9, 40, 240, 2, False), (6, 5, 80, 480, 5, True), (40, 40, 240, 40, 3, False), (160, 160, 16, 96, 6, True), '
+            '(80, 80, 144, 24, 7, False), (96, 96, 32, 16, 5, False), (31, 33, 256, 256, 9, True), (64, 64, 112, 64, 9, False)]:\n'
+            '    T.check(MG.pw_graph(h, w, cin, cout, act=act, seed=h + cin), B)\n'
+            'for (h, w, c, cmid, B) in [(8, 16, 16, 96, 1), (5, 7, 24, 144, 3), (20, 20, 40, 240, 2), (80, 80, 24, 144, 6)]:\n'
+            '    T.check(MG.pw_graph(h, w, c, cmid, act=True, residual=True, seed=c), B)\n'
+            % (os.path.dirname(here), here))
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, VBT_PW_PERSIST='1', VBT_PW_PERSIST_MIN_TILES='1'),
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+# ---- bf16 head contraction (BASELINE configs[3]): same integers on the kind::f16 tensor path ----
+
+@pytest.mark.parametrize('h,w,c,cout,kind', [
+    (3, 3, 64, 64, 0), (20, 20, 64, 64, 0), (40, 40, 64, 36, 2), (12, 12, 88, 88, 0), (48, 48, 88, 9, 1),
+    (7, 7, 112, 112, 0), (28, 28, 112, 112, 0), (56, 56, 112, 36, 2), (56, 56, 112, 9, 1), (9, 13, 16, 16, 0),
+    (11, 6, 128, 128, 0),
+])
+def test_fused_head_stage_bf16(h, w, c, cout, kind):
+    """DW3x3 -> PW with the pointwise stage as tcgen05.mma.kind::f16 (bf16 operands, fp32
+    accumulators): bit-identical to the int8 oracle, because every operand, product and partial
+    sum is an integer below 2^24."""
+    B = 2
+    g = MG.head_graph(h, w, c, cout, act=(kind == 0), seed=h * 100 + c, out_kind=kind)
+    g.head_dtype = 'bf16'
+    x, xp = MG.random_input(g, B, 4)
+    # extremes: -128 activations against +-127 weights everywhere in one frame
+    x[0], xp[0, ..., :c] = -128, -128
+    cls, box, want = OE.run(g, x, keep=True)
+    got = MG.run_gpu(g, xp)
+    assert list(MG.run_gpu.last_plan) == [2, 0]
+    if kind == 1:
+        assert np.array_equal(got[-1], cls)
+    elif kind == 2:
+        assert np.array_equal(got[-2], box)
+    else:
+        assert np.array_equal(got[g.ops[-1].out][0].astype(np.int16), want[g.ops[-1].out])

@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
   // ---- epilogue: thread t owns position mt*128 + t ---------------------------------------------
   const bool has_g1 = gp * 2 + 1 < a.groups;
   for (int mt = 0; mt < a.n_mt; ++mt) {
-    mbar_wait(smem_u32(&mbar[mt]), 0);
+    if (warp == 0) mbar_wait(smem_u32(&mbar[mt]), 0);   // one warp polls, the others sleep on the barrier
+    __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)mt * 32;
     uint32_t v[32];
@@ -197,8 +198,8 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
       for (int w4 = 0; w4 < 8; ++w4) {
         const int4 bq = *reinterpret_cast<const int4*>(sBias + w4 * 4);
         const float4 mq = *reinterpret_cast<const float4*>(sMult + w4 * 4);
-        packed[w4] = vbt::pack4_s8(a.rq((int)v[w4 * 4 + 0] + bq.x, mq.x), a.rq((int)v[w4 * 4 + 1] + bq.y, mq.y),
-                                   a.rq((int)v[w4 * 4 + 2] + bq.z, mq.z), a.rq((int)v[w4 * 4 + 3] + bq.w, mq.w));
+        packed[w4] = a.rq.pack4((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
+                                (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
       }
       int8_t* o = a.out + (((size_t)b * a.Ho + oy0 + ly) * a.Wo + lx) * a.c_p + gp * 32;
       *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
@@ -256,7 +257,7 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
   while (cols < a.n_mt * 32) cols <<= 1;
   a.tmem_cols = cols;
   a.inv_pw = (uint32_t)((0x100000000ULL + a.PW - 1) / a.PW);
-  a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
+  a.rq = Requant(op.zp_out, op.act_lo, op.act_hi, op.requant_fast);
   size_t smem = (size_t)op.stride * op.stride * 2 * a.plane_pos * 16 + (size_t)op.k * op.k * 1024;
   if (smem > 200 * 1024) return VBT_OK;
   const size_t cap_ctas = 512 / cols;                      // never more CTAs than TMEM can serve

@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 8;
+constexpr int kBlobVersion = 10;
 
 struct BlobHeader {
   uint32_t magic;
@@ -74,7 +74,9 @@ struct OpRecord {
   int32_t out_kind;        // 0 workspace tensor, 1 raw class output, 2 raw box output
   int32_t out_pix_stride;
   int32_t branch;          // 0: trunk (program order); k > 0: head chain k, independent of the others
-  int32_t reserved[6];
+  int32_t requant_fast;    // 1: |acc * mult| < 2^15 - 256 for every possible input (Requant::pack4)
+  int32_t pw_dtype;        // OP_PW inside a fused head stage: 0 int8 (kind::i8), 1 bf16 (kind::f16)
+  int32_t reserved[4];
 };
 static_assert(sizeof(OpRecord) == 224, "op record layout");
 

@@ -115,8 +115,7 @@ __global__ void __launch_bounds__(128) stem_kernel(StemArgs a) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 mv = *reinterpret_cast<const float4*>(sm + c0 + q * 4);
-        packed[q] = vbt::pack4_s8(a.rq(acc[q * 4 + 0], mv.x), a.rq(acc[q * 4 + 1], mv.y),
-                                  a.rq(acc[q * 4 + 2], mv.z), a.rq(acc[q * 4 + 3], mv.w));
+        packed[q] = a.rq.pack4(acc[q * 4 + 0], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3], mv.x, mv.y, mv.z, mv.w);
       }
       *reinterpret_cast<uint4*>(o + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     }
@@ -242,8 +241,7 @@ __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
               acc3 = __dp4a(xv, (int)wv.w, acc3);
             }
           }
-          out[out_off] = vbt::pack4_s8(a.rq(acc0, mult.x), a.rq(acc1, mult.y),
-                                       a.rq(acc2, mult.z), a.rq(acc3, mult.w));
+          out[out_off] = a.rq.pack4(acc0, acc1, acc2, acc3, mult.x, mult.y, mult.z, mult.w);
         }
         out_off += words;
       }
@@ -537,7 +535,7 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         a.mult = reinterpret_cast<const float*>(data(op.scale_off));
         a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out;
         a.cout_p = op.cout_p; a.pad_top = op.pad_top; a.pad_left = op.pad_left;
-        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
+        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi, op.requant_fast);
         VBT_REQUIRE(op.cout_p <= 64 && op.k == 3 && op.stride == 2, "vbt_detect: unsupported stem");
         VBT_CHECK_CUDA(launch_pdl(stem_kernel, dim3(grid_for((long long)B * op.h_out * op.w_out, 128)), dim3(128), 0, st, a));
         break;
@@ -553,7 +551,7 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         a.mult = reinterpret_cast<const float*>(data(op.scale_off));
         a.B = B; a.H = op.h_in; a.W = op.w_in; a.Ho = op.h_out; a.Wo = op.w_out; a.c_p = op.cout_p;
         a.pad_top = op.pad_top; a.pad_left = op.pad_left;
-        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi);
+        a.zp_in = op.zp_in[0]; a.rq = Requant(op.zp_out, op.act_lo, op.act_hi, op.requant_fast);
         int rc = VBT_OK;
         if (op.k == 3 && op.stride == 1) rc = launch_dw<3, 1>(a, st);
         else if (op.k == 3 && op.stride == 2) rc = launch_dw<3, 2>(a, st);
@@ -579,6 +577,8 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
         break;
       }
       case OP_PW: {
+        VBT_REQUIRE(op.pw_dtype == 0, "vbt_detect: bf16 pointwise op %d is not inside a fused head stage "
+                    "(csrc/node_umma.cu); there is no stand-alone bf16 kernel", oi);
         const int8_t* in = tensor_ptr(op.in[0]);
         const int8_t* res = (op.n_in == 2) ? tensor_ptr(op.in[1]) : nullptr;
         int8_t* out;

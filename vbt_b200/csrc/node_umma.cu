@@ -19,6 +19,11 @@
 //      core matrix, the next channel group one plane further), so the 1x1 conv is
 //      ceil(groups/2) tcgen05.mma per tile against the [Cout][C] weights, reusing the TMEM
 //      columns; the epilogue requantises (+ LOGISTIC LUT for the class head) and stores.
+// bf16 heads (BASELINE configs[3], OpRecord.pw_dtype = 1): the pointwise stage runs as
+// tcgen05.mma.kind::f16 on bf16 operands with fp32 accumulators.  The operands are the SAME
+// integers (|x| <= 128, |w| <= 127: exact in bf16; every product and every partial sum of
+// <= 128 terms stays below 2^24: exact in fp32), so the accumulators -- and therefore the
+// outputs -- equal the int8 path's bit for bit; only the tensor-pipe data type changes.
 #include "model.cuh"
 #include "requant.cuh"
 
@@ -41,7 +46,7 @@ struct NodeArgs {
   const int8_t* wdiag; const int32_t* dw_bias; const float* dw_mult; vbt::Requant dw_rq; int dw_zp_in;
   // pointwise
   const int8_t* pw_w; const int32_t* pw_bias; const float* pw_mult; vbt::Requant pw_rq; const int8_t* lut;
-  int cout, cout_p;
+  int cout, cout_p, pw_bf16;
   int8_t* out; int out_pix_stride; long long out_batch_stride, out_elem_offset; int vector_out;
   // tiling
   int TH, n_bands, PW, n_mt, rows_alloc, plane_pos, tmem_cols;
@@ -64,6 +69,24 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
       "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
 }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+// 8 int8 (two words) -> 8 bf16: float(v) of |v| <= 128 has its whole significand in the upper half
+__device__ __forceinline__ uint4 s8x8_to_bf16(uint32_t w0, uint32_t w1) {
+  uint32_t f[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[i] = __float_as_uint(__int2float_rn((int)(int8_t)(w0 >> (8 * i))));
+    f[4 + i] = __float_as_uint(__int2float_rn((int)(int8_t)(w1 >> (8 * i))));
+  }
+  return make_uint4(__byte_perm(f[0], f[1], 0x7632), __byte_perm(f[2], f[3], 0x7632),
+                    __byte_perm(f[4], f[5], 0x7632), __byte_perm(f[6], f[7], 0x7632));
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
                : "memory");
@@ -77,6 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     if (spin > (1LL << 24)) __trap();
   }
+}
+// one warp polls the mbarrier, the others sleep on the hardware barrier instead of spinning
+// through issue slots the epilogues of co-resident CTAs could use
+__device__ __forceinline__ void block_wait(uint32_t bar, uint32_t parity, int warp) {
+  if (warp == 0) mbar_wait(bar, parity);
+  __syncthreads();
 }
 __device__ __forceinline__ void st_shared16(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
@@ -130,8 +159,10 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   const uint32_t mid_plane = (uint32_t)a.n_mt * 128 * 16; // bytes per depthwise-output plane
   unsigned char* pin = smem;                                        // [Ge][plane_pos][16]
   unsigned char* pmid = pin + (size_t)Ge * in_plane;                // [Ge][n_mt*128][16]
-  unsigned char* wdw = pmid + (size_t)Ge * mid_plane;               // [pairs][9][1024]
-  unsigned char* wpw = wdw + (size_t)a.pairs * 9 * 1024;            // [cout_p/8][Ge][8][16]
+  // bf16 pointwise stage: one plane per 8 channels ([2G][n_mt*128][16 B]) and bf16 weights
+  const int mid_planes = a.pw_bf16 ? 2 * G : Ge;
+  unsigned char* wdw = pmid + (size_t)mid_planes * mid_plane;       // [pairs][9][1024]
+  unsigned char* wpw = wdw + (size_t)a.pairs * 9 * 1024;            // [cout_p/8][Ge | 2G][8][16]
   const int oy0 = band * a.TH;
   const int th = min(a.TH, a.H - oy0);
 
@@ -156,20 +187,32 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
     for (int i = tid; i < a.pairs * 9 * 64; i += kThreads)
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(wdw) + (uint32_t)i * 16), "l"(src + i));
     // pointwise weights [cout_p][c_p] -> core matrices: item ((g*Ge + kc)*8 + rr), row g*8+rr, chunk kc
-    const int items = (a.cout_p / 8) * Ge * 8;
-    for (int it = tid; it < items; it += kThreads) {
-      const int rr = it & 7, q = it >> 3;
-      const int g = q / Ge, kc = q - g * Ge;
-      const uint32_t dst = smem_u32(wpw) + (uint32_t)it * 16;
-      if (kc < G) {
-        const int8_t* src2 = a.pw_w + (size_t)(g * 8 + rr) * a.c_p + kc * 16;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src2));
-      } else {
-        st_shared16(dst, make_uint4(0, 0, 0, 0));
+    if (!a.pw_bf16) {
+      const int items = (a.cout_p / 8) * Ge * 8;
+      for (int it = tid; it < items; it += kThreads) {
+        const int rr = it & 7, q = it >> 3;
+        const int g = q / Ge, kc = q - g * Ge;
+        const uint32_t dst = smem_u32(wpw) + (uint32_t)it * 16;
+        if (kc < G) {
+          const int8_t* src2 = a.pw_w + (size_t)(g * 8 + rr) * a.c_p + kc * 16;
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src2));
+        } else {
+          st_shared16(dst, make_uint4(0, 0, 0, 0));
+        }
+      }
+    } else {                                           // the same integers as bf16, 8 channels per 16 B
+      const int items = (a.cout_p / 8) * G * 8;
+      for (int it = tid; it < items; it += kThreads) {
+        const int rr = it & 7, q = it >> 3;
+        const int g = q / G, kc = q - g * G;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(a.pw_w + (size_t)(g * 8 + rr) * a.c_p + kc * 16));
+        const uint32_t dst = smem_u32(wpw) + (uint32_t)(((g * 2 * G + 2 * kc) * 8 + rr) * 16);
+        st_shared16(dst, s8x8_to_bf16(w.x, w.y));
+        st_shared16(dst + 128, s8x8_to_bf16(w.z, w.w));
       }
     }
   }
-  if (Ge > G)                                          // pad group of the depthwise output: zeros
+  if (Ge > G && !a.pw_bf16)                            // pad group of the depthwise output: zeros
     for (int i = tid; i < a.n_mt * 128; i += kThreads)
       st_shared16(smem_u32(pmid) + (uint32_t)(Ge - 1) * mid_plane + (uint32_t)i * 16, make_uint4(0, 0, 0, 0));
   vbt::pdl_wait();
@@ -246,7 +289,7 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   }
   // depthwise epilogue: requantise into the middle planes (every position, valid or not)
   for (int mt = 0; mt < a.n_mt; ++mt) {
-    mbar_wait(smem_u32(&mbar_dw[mt]), 0);
+    block_wait(smem_u32(&mbar_dw[mt]), 0, warp);
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     for (int p = 0; p < a.pairs; ++p) {
       const int grp = 2 * p + half;                    // this warp half requantises one 16-channel group
@@ -265,11 +308,17 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
       for (int w4 = 0; w4 < 4; ++w4) {
         const int4 bq = *reinterpret_cast<const int4*>(sDwBias + grp * 16 + w4 * 4);
         const float4 mq = *reinterpret_cast<const float4*>(sDwMult + grp * 16 + w4 * 4);
-        packed[w4] = vbt::pack4_s8(a.dw_rq((int)v[w4 * 4 + 0] + bq.x, mq.x), a.dw_rq((int)v[w4 * 4 + 1] + bq.y, mq.y),
-                                   a.dw_rq((int)v[w4 * 4 + 2] + bq.z, mq.z), a.dw_rq((int)v[w4 * 4 + 3] + bq.w, mq.w));
+        packed[w4] = a.dw_rq.pack4((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
+                                   (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
       }
-      st_shared16(smem_u32(pmid) + (uint32_t)grp * mid_plane + (uint32_t)(mt * 128 + row) * 16,
-                  make_uint4(packed[0], packed[1], packed[2], packed[3]));
+      if (!a.pw_bf16) {
+        st_shared16(smem_u32(pmid) + (uint32_t)grp * mid_plane + (uint32_t)(mt * 128 + row) * 16,
+                    make_uint4(packed[0], packed[1], packed[2], packed[3]));
+      } else {
+        const uint32_t dst = smem_u32(pmid) + (uint32_t)(2 * grp) * mid_plane + (uint32_t)(mt * 128 + row) * 16;
+        st_shared16(dst, s8x8_to_bf16(packed[0], packed[1]));
+        st_shared16(dst + mid_plane, s8x8_to_bf16(packed[2], packed[3]));
+      }
     }
   }
   // the middle planes are the pointwise A operand; the depthwise TMEM columns are free again
@@ -282,16 +331,25 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   if (tid == 0) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cout_p >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t abase = smem_u32(pmid), bbase = smem_u32(wpw);
+    // bf16: D = F32, A = B = BF16; one MMA (K = 16 elements) per 16-channel group
+    const uint32_t idesc16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cout_p >> 3) << 17) | ((128u >> 4) << 24);
     for (int mt = 0; mt < a.n_mt; ++mt) {
-      for (int k2 = 0; k2 < Ge / 2; ++k2)
-        umma_i8(tmem + (uint32_t)mt * a.cout_p,
-                umma_desc(abase + (uint32_t)(2 * k2) * mid_plane + (uint32_t)mt * 2048, mid_plane, 128),
-                umma_desc(bbase + (uint32_t)k2 * 256, 128, (uint32_t)Ge * 128), idesc, k2 > 0 ? 1u : 0u);
+      if (!a.pw_bf16) {
+        for (int k2 = 0; k2 < Ge / 2; ++k2)
+          umma_i8(tmem + (uint32_t)mt * a.cout_p,
+                  umma_desc(abase + (uint32_t)(2 * k2) * mid_plane + (uint32_t)mt * 2048, mid_plane, 128),
+                  umma_desc(bbase + (uint32_t)k2 * 256, 128, (uint32_t)Ge * 128), idesc, k2 > 0 ? 1u : 0u);
+      } else {
+        for (int g = 0; g < G; ++g)
+          umma_f16(tmem + (uint32_t)mt * a.cout_p,
+                   umma_desc(abase + (uint32_t)(2 * g) * mid_plane + (uint32_t)mt * 2048, mid_plane, 128),
+                   umma_desc(bbase + (uint32_t)g * 256, 128, (uint32_t)(2 * G) * 128), idesc16, g > 0 ? 1u : 0u);
+      }
       umma_commit(smem_u32(&mbar_pw[mt]));
     }
   }
   for (int mt = 0; mt < a.n_mt; ++mt) {
-    mbar_wait(smem_u32(&mbar_pw[mt]), 0);
+    block_wait(smem_u32(&mbar_pw[mt]), 0, warp);
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     const int q = mt * 128 + row;
     const int ly = (int)__umulhi((uint32_t)q, a.inv_pw);
@@ -310,24 +368,27 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
       if (!valid) continue;
-      int y[16];
+      if (a.pw_bf16) {                                 // fp32 accumulators hold exact integers
 #pragma unroll
-      for (int w4 = 0; w4 < 4; ++w4) {
-        const int4 bq = *reinterpret_cast<const int4*>(sPwBias + c0 + w4 * 4);
-        const float4 mq = *reinterpret_cast<const float4*>(sPwMult + c0 + w4 * 4);
-        y[w4 * 4 + 0] = a.pw_rq((int)v[w4 * 4 + 0] + bq.x, mq.x);
-        y[w4 * 4 + 1] = a.pw_rq((int)v[w4 * 4 + 1] + bq.y, mq.y);
-        y[w4 * 4 + 2] = a.pw_rq((int)v[w4 * 4 + 2] + bq.z, mq.z);
-        y[w4 * 4 + 3] = a.pw_rq((int)v[w4 * 4 + 3] + bq.w, mq.w);
+        for (int j = 0; j < 16; ++j) v[j] = (uint32_t)__float2int_rn(__uint_as_float(v[j]));
       }
       if (a.vector_out) {
-        *reinterpret_cast<uint4*>(o + c0) =
-            make_uint4(vbt::pack4_s8(y[0], y[1], y[2], y[3]), vbt::pack4_s8(y[4], y[5], y[6], y[7]),
-                       vbt::pack4_s8(y[8], y[9], y[10], y[11]), vbt::pack4_s8(y[12], y[13], y[14], y[15]));
+        uint32_t packed[4];
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          const int4 bq = *reinterpret_cast<const int4*>(sPwBias + c0 + w4 * 4);
+          const float4 mq = *reinterpret_cast<const float4*>(sPwMult + c0 + w4 * 4);
+          packed[w4] = a.pw_rq.pack4((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
+                                     (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
+        }
+        *reinterpret_cast<uint4*>(o + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
       } else {                                         // packed head outputs (9 / 36 channels per pixel)
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c0 + j < a.cout) o[c0 + j] = a.lut ? a.lut[y[j] + 128] : (int8_t)y[j];
+        for (int j = 0; j < 16; ++j) {
+          if (c0 + j >= a.cout) break;
+          const int y = a.pw_rq((int)v[j] + sPwBias[c0 + j], sPwMult[c0 + j]);
+          o[c0 + j] = a.lut ? a.lut[y + 128] : (int8_t)y;
+        }
       }
     }
   }
@@ -364,14 +425,14 @@ int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw
   a.wdiag = reinterpret_cast<const int8_t*>(m->dev_data + dw.lut_off);
   a.dw_bias = reinterpret_cast<const int32_t*>(m->dev_data + dw.bias_off);
   a.dw_mult = reinterpret_cast<const float*>(m->dev_data + dw.scale_off);
-  a.dw_rq = Requant(dw.zp_out, dw.act_lo, dw.act_hi);
+  a.dw_rq = Requant(dw.zp_out, dw.act_lo, dw.act_hi, dw.requant_fast);
   a.dw_zp_in = dw.zp_in[0];
   a.pw_w = reinterpret_cast<const int8_t*>(m->dev_data + pw.w_off);
   a.pw_bias = reinterpret_cast<const int32_t*>(m->dev_data + pw.bias_off);
   a.pw_mult = reinterpret_cast<const float*>(m->dev_data + pw.scale_off);
-  a.pw_rq = Requant(pw.zp_out, pw.act_lo, pw.act_hi);
+  a.pw_rq = Requant(pw.zp_out, pw.act_lo, pw.act_hi, pw.requant_fast);
   a.lut = pw.lut_off >= 0 ? reinterpret_cast<const int8_t*>(m->dev_data + pw.lut_off) : nullptr;
-  a.cout = pw.cout; a.cout_p = pw.cout_p;
+  a.cout = pw.cout; a.cout_p = pw.cout_p; a.pw_bf16 = pw.pw_dtype == 1;
   a.out = out; a.out_pix_stride = pw.out_pix_stride; a.out_batch_stride = out_batch_stride;
   a.out_elem_offset = pw.out_elem_offset; a.vector_out = (pw.out_kind == 0);
   // tiling: bands of whole rows, at most kMaxTiles tiles; TMEM = max(depthwise, pointwise) columns
@@ -397,8 +458,9 @@ int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw
   while (cols < std::max(a.pairs * 32, a.cout_p) * a.n_mt) cols <<= 1;
   a.tmem_cols = cols;
   a.inv_pw = (uint32_t)((0x100000000ULL + a.PW - 1) / a.PW);
-  size_t smem = (size_t)a.kch_pad * a.plane_pos * 16 + (size_t)a.kch_pad * a.n_mt * 2048 +
-                (size_t)a.pairs * 9 * 1024 + (size_t)a.cout_p * a.kch_pad * 16;
+  const int mid_planes = a.pw_bf16 ? 2 * a.groups : a.kch_pad;
+  size_t smem = (size_t)a.kch_pad * a.plane_pos * 16 + (size_t)mid_planes * a.n_mt * 2048 +
+                (size_t)a.pairs * 9 * 1024 + (size_t)a.cout_p * mid_planes * 16;
   if (smem > 200 * 1024) return VBT_OK;
   smem = std::max(smem, (size_t)228 * 1024 / (512 / cols + 1));
   static bool attr_set = false;

@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(NT) pw_umma_kernel(PwUmmaArgs a) {
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(
           smem_u32(&mbar)) : "memory");
     }
-    mbar_wait(smem_u32(&mbar), parity);               // MMAs done: smem reusable, TMEM readable
+    // MMAs done: smem reusable, TMEM readable.  One warp polls the mbarrier; the rest sleep on the
+    // hardware barrier instead of spinning through issue slots co-resident CTAs' epilogues need
+    if (warp == 0) mbar_wait(smem_u32(&mbar), parity);
+    __syncthreads();
     parity ^= 1;
   }
   asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -220,19 +223,22 @@ __global__ void __launch_bounds__(NT) pw_umma_kernel(PwUmmaArgs a) {
     for (int q = 0; q < 4; ++q) {
       const int4 bq = *reinterpret_cast<const int4*>(sBias + c0 + q * 4);
       const float4 mq = *reinterpret_cast<const float4*>(sMult + c0 + q * 4);
-      const int bs[4] = {bq.x, bq.y, bq.z, bq.w};
-      const float ms[4] = {mq.x, mq.y, mq.z, mq.w};
-      int y[4];
+      if (!HAS_RES) {
+        packed[q] = a.rq.pack4((int)v[q * 4 + 0] + bq.x, (int)v[q * 4 + 1] + bq.y, (int)v[q * 4 + 2] + bq.z,
+                               (int)v[q * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
+      } else {
+        const int bs[4] = {bq.x, bq.y, bq.z, bq.w};
+        const float ms[4] = {mq.x, mq.y, mq.z, mq.w};
+        int y[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        y[j] = a.rq((int)v[q * 4 + j] + bs[j], ms[j]);
-        if (HAS_RES) {
+        for (int j = 0; j < 4; ++j) {
+          y[j] = a.rq((int)v[q * 4 + j] + bs[j], ms[j]);
           const int r = (int)(int8_t)(rw[q] >> (8 * j));
           const int s = (y[j] - a.zp_conv) * a.add_mult0 + (r - a.res_zp) * a.add_mult1 + round;
           y[j] = clampi((s >> a.add_shift) + a.zp_final, a.lo, a.hi);
         }
+        packed[q] = vbt::pack4_s8(y[0], y[1], y[2], y[3]);
       }
-      packed[q] = vbt::pack4_s8(y[0], y[1], y[2], y[3]);
     }
     *reinterpret_cast<uint4*>(orow + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
@@ -265,6 +271,9 @@ int pw_impl_from_env() {
 
 namespace vbt {
 
+int launch_pw_persist(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res, int8_t* out,
+                      int B, cudaStream_t st, bool* taken);
+
 int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res, int8_t* out,
                    long long out_batch_stride, int B, cudaStream_t st, bool* taken) {
   static const int impl = pw_impl_from_env();
@@ -272,6 +281,9 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   // the packed head outputs (9 / 36 channels per pixel, LOGISTIC LUT) stay on the SIMT kernel
   if (!impl || op.out_kind != 0 || op.lut_off >= 0) return VBT_OK;
   if (op.cin_p % 16 || op.cout_p % 16 || op.cout_p < 16) return VBT_OK;
+  // large-M, small-K layers: the persistent warp-specialised kernel (pw_persist.cu)
+  if (int rc = launch_pw_persist(m, op, in, res, out, B, st, taken)) return rc;
+  if (*taken) return VBT_OK;
   PwUmmaArgs a;
   a.in = in; a.res = res; a.out = out;
   a.w = reinterpret_cast<const int8_t*>(m->dev_data + op.w_off);
@@ -292,7 +304,7 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   a.add_mult0 = op.add_mult[0]; a.add_mult1 = op.add_mult[1]; a.add_shift = op.add_shift;
   a.zp_final = op.zp_in[2];
   // with a residual the conv result is an int8 intermediate: saturate, clamp after the add
-  a.rq = has_res ? Requant(op.zp_out, -128, 127) : Requant(op.zp_out, op.act_lo, op.act_hi);
+  a.rq = has_res ? Requant(op.zp_out, -128, 127) : Requant(op.zp_out, op.act_lo, op.act_hi, op.requant_fast);
   a.out_stride = ((a.nc / 16) | 1) * 16;
   int cols = 32;
   while (cols < a.nc) cols <<= 1;

@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 8
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 10
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -595,7 +595,8 @@ def _pack_op(rec):
     out += struct.pack('<5q', f['w_off'], f['bias_off'], f['scale_off'], f['lut_off'],
                        f['out_elem_offset'])
     out += struct.pack('<3i i 3i 3i 3i ii 7i', *f['add_mult'], f['add_shift'], *f['resample'],
-                       *f['in_h'], *f['in_w'], f['out_kind'], f['out_pix_stride'], f['branch'], *([0] * 6))
+                       *f['in_h'], *f['in_w'], f['out_kind'], f['out_pix_stride'], f['branch'],
+                       f.get('requant_fast', 0), f.get('pw_dtype', 0), *([0] * 4))
     return out
 
 
@@ -678,6 +679,11 @@ def pack_blob(g: Graph):
             mult = np.zeros(cout_p, np.float32)
             mult[:cout] = q['mult']
             r['w_off'], r['bias_off'], r['scale_off'] = put(wp), put(bias), put(mult)
+            # the kernels' packed requantisation carries rint(acc * M) in 16-bit lanes: allowed only
+            # where no input can push |acc * M| past 2^15 - 256 (csrc/requant.cuh)
+            wabs = np.abs(w).reshape(cout, -1).sum(axis=1)
+            bound = (255.0 * wabs + np.abs(q['bias'].astype(np.float64))) * np.abs(q['mult'].astype(np.float64))
+            r['requant_fast'] = int(bound.max() < 32000.0)
             r['zp_out'] = q['conv_zp_out']
             if op.type == OP_PW and op.residual >= 0:
                 r['in'][1] = op.residual
@@ -694,6 +700,9 @@ def pack_blob(g: Graph):
         elif op.type == OP_ADD:
             r['add_mult'] = (q['add_mult'] + [0, 0, 0])[:3]
             r['add_shift'] = q['add_shift']
+        if op.type == OP_PW and getattr(g, 'head_dtype', 'int8') == 'bf16' and \
+                (op.branch > 0 or getattr(g, 'variant', '') == 'micro'):
+            r['pw_dtype'] = 1          # head contraction on the bf16 tensor path (same integers)
         if op.out_kind == 1:
             r['out_pix_stride'] = a_per * NUM_CLASSES
             r['out_elem_offset'] = op.level_offset * NUM_CLASSES
@@ -716,9 +725,13 @@ def pack_blob(g: Graph):
     return bytes(blob)
 
 
-def build_synthetic(variant='lite0', seed=1234, calib_frames=None, n_calib=4):
-    """Seeded synthetic model: float init -> PTQ calibration -> quantised Graph."""
+def build_synthetic(variant='lite0', seed=1234, calib_frames=None, n_calib=4, head_dtype='int8'):
+    """Seeded synthetic model: float init -> PTQ calibration -> quantised Graph.
+    head_dtype: 'int8' or 'bf16' -- the tensor-core data type of the class / box nets' pointwise
+    convs (BASELINE.json configs[3]); the quantised model and its outputs are the same."""
+    assert head_dtype in ('int8', 'bf16')
     g = Graph(variant)
+    g.head_dtype = head_dtype
     init_weights(g, seed)
     if calib_frames is None:
         from .synth import synthetic_model_inputs
