@@ -258,3 +258,30 @@ def test_video_pipeline_equals_oracle_chain():
         got = np.array([[p.time_start, p.time_end, p.y_start, p.y_end, p.rom, p.type]
                         for p in phases]).reshape(-1, 6)
         assert np.array_equal(got, w)
+
+
+def test_interpreter_loads_a_tflite_file(tmp_path):
+    """track.py:93 `Interpreter(model_path=<x.tflite>)`: the exported synthetic Lite0 loaded back
+    through vbt_b200.tflite_reader gives the detections of the in-memory graph."""
+    from vbt_b200.interpreter import Interpreter
+    from vbt_b200.odt import run_odt
+    from vbt_b200.synth import synthetic_model_inputs
+    from vbt_b200 import tflite_writer
+    g, _ = model('lite0')
+    path = str(tmp_path / 'efficientdet_lite0_synthetic.tflite')
+    tflite_writer.save(g, path)
+    a, b = Interpreter(model_path=g, num_threads=4), Interpreter(model_path=path, num_threads=4)
+    a.allocate_tensors(); b.allocate_tensors()
+    assert list(b.get_input_details()[0]['shape']) == [1, 320, 320, 3]
+    x = synthetic_model_inputs(2, g.S, seed=33)
+    for img in x:
+        ra = a.get_signature_runner()(images=img[None])
+        rb = b.get_signature_runner()(images=img[None])
+        for k in ('output_0', 'output_1', 'output_2', 'output_3'):
+            assert np.array_equal(ra[k], rb[k]), k
+        la, lb = run_odt(img, a, 0.3), run_odt(img, b, 0.3)
+        assert len(la) == len(lb)
+        for p, q in zip(la, lb):
+            assert np.array_equal(p['bounding_box'], q['bounding_box']) and p['score'] == q['score']
+    with pytest.raises(ValueError):
+        Interpreter(model_path=str(tmp_path / 'missing.tflite'))

@@ -143,7 +143,7 @@ class Graph:
         self.ops.append(Op(OP_MAXPOOL, [x], o, k=3, stride=2, name=name))
         return o
 
-    def _fuse(self, xs, level_hw, name):
+    def _fuse(self, xs, level_hw, name, act=True):
         h, w = level_hw
         rs = []
         for x in xs:
@@ -156,7 +156,7 @@ class Graph:
                 assert same_pad(t.h, 3, 2)[0] == h, 'only one pooling step between levels'
                 rs.append(RS_DOWN)
         o = self._t(h, w, self.tensors[xs[0]].c, name)
-        self.ops.append(Op(OP_ADD, list(xs), o, act=True, resample=rs, name=name))
+        self.ops.append(Op(OP_ADD, list(xs), o, act=act, resample=rs, name=name))
         return o
 
     # -- the network -------------------------------------------------------------------
@@ -204,6 +204,11 @@ class Graph:
                         src = self._pw(src, C, False, f'fpn{cell}.n{ni}.lat{j}')
                     xs.append(src)
                 name = f'fpn{cell}.n{ni}'
+                # tf.add_n of three inputs reaches the exported graph as a tree of binary ADDs
+                # (the converter lowers AddN; int8 ADD_N does not exist), each with its own
+                # output quantisation: ADD(ADD(a, b), c), the activation on the last one
+                if len(xs) == 3:
+                    xs = [self._fuse(xs[:2], lvl_hw[level], name + '.sum0', act=False), xs[2]]
                 f = self._fuse(xs, lvl_hw[level], name + '.sum')
                 d = self._dw(f, 3, 1, False, name + '.dw')
                 local.append(self._pw(d, C, False, name + '.pw'))
@@ -232,7 +237,10 @@ class Graph:
     # -- anchors ---------------------------------------------------
     def anchors(self):
         """f32 [N,4] (ycentre, xcentre, h, w), normalised, level-major then y, x, then
-        octave-major / aspect-minor."""
+        octave-major / aspect-minor.  A graph imported from a .tflite file carries the file's own
+        anchor tensor (`anchor_table`)."""
+        if getattr(self, 'anchor_table', None) is not None:
+            return np.asarray(self.anchor_table, dtype=np.float32)
         out = []
         S = float(self.S)
         for (h, w) in self.level_sizes:
@@ -445,6 +453,8 @@ def quantize(g: Graph, calib_frames):
             q['bias'] = np.rint(op.bias / (si * sw)).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
             q['mult'] = (np.float64(si) * sw / np.float64(conv_so)).astype(np.float32)
             q['conv_zp_out'] = conv_zo
+            q['w_scale'] = sw.astype(np.float32)          # per-channel filter scales (.tflite export)
+            q['pre_scale'] = float(np.float32(conv_so))   # scale of the conv's own int8 result
             if op.out_kind == 1:       # LOGISTIC fused behind the class conv
                 qs = np.arange(-128, 128)
                 real = (qs - zo) * so
