@@ -330,8 +330,33 @@ def main():
                 stage_ms[nme] += a.elapsed_time(b_)
     kern = {}
     frames_prof = prof_frames
-    for op, tms in zip(g.ops, op_ms):
+    # launch plan: a fused [ADD ->] DW3x3 -> PW run is ONE kernel (csrc/node_umma.cu) whose device
+    # time is recorded on its first op; its algorithmic bytes are the run's inputs + its output +
+    # the weights -- the intermediates never leave the SM
+    plan = det.plan()
+    op_class = []
+    for i, op in enumerate(g.ops):
         name, by, fl = op_algorithmic(g, op, effdet)
+        if plan[i] > 1:
+            run = g.ops[i:i + plan[i]]
+            name = 'node_fused'
+            first_in = sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c for t in run[0].inputs)
+            last = run[-1]
+            t_in = g.tensors[last.inputs[0]]
+            out_el = (g.tensors[last.out].h * g.tensors[last.out].w * g.tensors[last.out].c) if last.out >= 0 \
+                else t_in.h * t_in.w * g.out_channels(last)
+            wts = sum(op_algorithmic(g, o, effdet)[1] - sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c for t in o.inputs)
+                      - ((g.tensors[o.out].h * g.tensors[o.out].w * g.tensors[o.out].c) if o.out >= 0
+                         else g.tensors[o.inputs[0]].h * g.tensors[o.inputs[0]].w * g.out_channels(o))
+                      for o in run if o.type != effdet.OP_ADD)
+            by = first_in + out_el + wts
+            fl = sum(op_algorithmic(g, o, effdet)[2] for o in run)
+        elif plan[i] == 0:
+            name, by, fl = None, 0, 0
+        op_class.append((name, by, fl))
+    for (name, by, fl), tms in zip(op_class, op_ms):
+        if name is None:
+            continue
         k = kern.setdefault(name, {'ms': 0.0, 'bytes_per_frame': 0, 'flops_per_frame': 0, 'launches_per_step': 0})
         k['ms'] += float(tms); k['bytes_per_frame'] += by; k['flops_per_frame'] += fl
         k['launches_per_step'] += 1
@@ -339,7 +364,9 @@ def main():
         with open(args.op_dump, 'w') as f:
             f.write('op\tkernel\tname\tin_hw\tcin\tcout\tus_per_call\talg_GBs\talg_TOPs\n')
             for i, (op, tms) in enumerate(zip(g.ops, op_ms)):
-                name, by, fl = op_algorithmic(g, op, effdet)
+                name, by, fl = op_class[i]
+                if name is None:
+                    name, by, fl = '(fused)', 0, 0
                 t_in = g.tensors[op.inputs[0]]
                 us = 1e3 * float(tms) / max(calls, 1)
                 f.write(f'{i}\t{name}\t{op.name}\t{t_in.h}x{t_in.w}\t{t_in.c}\t{g.out_channels(op)}\t{us:.2f}\t'

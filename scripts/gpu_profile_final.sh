@@ -15,3 +15,7 @@ timeout 900 ncu --profile-from-start off --set full --clock-control none --impor
     -o gpurun_out/${TAG}_prof_pw_umma python bench.py $ARGS > gpurun_out/${TAG}_ncu_pw.log 2>&1
 tail -2 gpurun_out/${TAG}_ncu_pw.log
 ls -la gpurun_out/ | tail -8
+# (4) the fused BiFPN-node / head-stage kernel: first four launches (5x5 ... 40x40 nodes of cell 0)
+timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:node_umma -s 0 -c 4 \
+    -o gpurun_out/${TAG}_prof_node_umma python bench.py $ARGS > gpurun_out/${TAG}_ncu_node.log 2>&1
+tail -2 gpurun_out/${TAG}_ncu_node.log

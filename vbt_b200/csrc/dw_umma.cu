@@ -73,6 +73,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[kMaxTiles];
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
       for (int w4 = 0; w4 < 8; ++w4) {
         const int4 bq = *reinterpret_cast<const int4*>(sBias + w4 * 4);
         const float4 mq = *reinterpret_cast<const float4*>(sMult + w4 * 4);
-        packed[w4] = a.rq.pack4((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
+        packed[w4] = a.rq.pack4t<FAST>((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
                                 (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
       }
       int8_t* o = a.out + (((size_t)b * a.Ho + oy0 + ly) * a.Wo + lx) * a.c_p + gp * 32;
@@ -264,11 +265,13 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
   smem = std::max(smem, (size_t)228 * 1024 / (cap_ctas + 1));
   static bool attr_set = false;
   if (!attr_set) {
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   dim3 grid((unsigned)a.n_bands, (unsigned)a.pairs, (unsigned)B);
-  VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel, grid, dim3(128), smem, st, a));
+  if (a.rq.fast) VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<true>, grid, dim3(128), smem, st, a));
+  else VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<false>, grid, dim3(128), smem, st, a));
   *taken = true;
   return VBT_OK;
 }

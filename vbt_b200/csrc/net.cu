@@ -144,7 +144,7 @@ struct DwArgs {
   vbt::Requant rq;
 };
 
-template <int K, int S>
+template <int K, int S, bool FAST>
 __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
   constexpr int J = (K == 5) ? (S == 1 ? 4 : 2) : (S == 1 ? 4 : 2);     // outputs per group
   constexpr bool kSmemW = (K == 5);   // 5x5: the 100 weight words live in shared memory, not registers
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) dw_kernel(DwArgs a) {
               acc3 = __dp4a(xv, (int)wv.w, acc3);
             }
           }
-          out[out_off] = a.rq.pack4(acc0, acc1, acc2, acc3, mult.x, mult.y, mult.z, mult.w);
+          out[out_off] = a.rq.pack4t<FAST>(acc0, acc1, acc2, acc3, mult.x, mult.y, mult.z, mult.w);
         }
         out_off += words;
       }
@@ -271,11 +271,13 @@ int launch_dw(DwArgs a, cudaStream_t st) {
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
-      VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_kernel<K, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_kernel<K, S, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+      VBT_CHECK_CUDA(cudaFuncSetAttribute(dw_kernel<K, S, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
       attr_set = true;
     }
   }
-  VBT_CHECK_CUDA(vbt::launch_pdl(dw_kernel<K, S>, grid, dim3(threads), smem, st, a));
+  if (a.rq.fast) VBT_CHECK_CUDA(vbt::launch_pdl(dw_kernel<K, S, true>, grid, dim3(threads), smem, st, a));
+  else VBT_CHECK_CUDA(vbt::launch_pdl(dw_kernel<K, S, false>, grid, dim3(threads), smem, st, a));
   return VBT_OK;
 }
 

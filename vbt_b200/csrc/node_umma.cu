@@ -40,6 +40,7 @@ struct NodeArgs {
   int n_in, fused_add;             // fused_add = 0: plain copy of in[0]
   int in_h[3], in_w[3], resample[3], zp_in[3], add_mult[3];
   int add_shift, add_zp, add_lo, add_hi;
+  int add_init;                    // rounding constant minus sum_i zp_i * mult_i (the zero points folded out)
   // geometry (depthwise 3x3 stride 1: output size = input size)
   int B, H, W, c_p, groups, pairs, kch_pad;
   // depthwise
@@ -111,6 +112,13 @@ __device__ __forceinline__ void st_shared16(uint32_t addr, uint4 v) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
 __device__ __forceinline__ int s8(uint32_t word, int i) { return (int)(int8_t)(word >> (8 * i)); }
+// byte J of a word, sign-extended: one PRMT (selector bit 3 replicates the byte's sign)
+template <int J>
+__device__ __forceinline__ int sext_byte(uint32_t word) {
+  uint32_t r;      // prmt.b32 directly: the __byte_perm intrinsic only honours three selector bits
+  asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(word), "n"(J | ((J | 8) << 4) | ((J | 8) << 8) | ((J | 8) << 12)));
+  return (int)r;
+}
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
 // one input of the BiFPN fusion at level position (oy, ox), 16 channels from c0
@@ -222,7 +230,6 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   {
     const uint32_t zpw = (uint32_t)(a.dw_zp_in & 0xff) * 0x01010101u;
     const int n_slots = a.rows_alloc * a.PW;
-    const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
     for (int i = tid; i < n_slots * G; i += kThreads) {
       const int g = i % G, slot = i / G;               // groups fastest: 16 B x G contiguous in global
       const int ly = (int)__umulhi((uint32_t)slot, a.inv_pw);
@@ -237,15 +244,19 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
       } else {
         int acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = round;
+        for (int j = 0; j < 16; ++j) acc[j] = a.add_init;
         for (int n = 0; n < a.n_in; ++n) {
           const uint4 v = fetch_resampled(a.in[n], b, iy, ix, a.H, a.W, a.in_h[n], a.in_w[n], a.resample[n],
                                           a.c_p, g * 16);
           const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+          const int mlt = a.add_mult[n];
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[q * 4 + j] += (s8(xs[q], j) - a.zp_in[n]) * a.add_mult[n];
+          for (int q = 0; q < 4; ++q) {                // sum_i (x_i - zp_i) * m_i = sum_i x_i * m_i + add_init
+            acc[q * 4 + 0] += sext_byte<0>(xs[q]) * mlt;
+            acc[q * 4 + 1] += sext_byte<1>(xs[q]) * mlt;
+            acc[q * 4 + 2] += sext_byte<2>(xs[q]) * mlt;
+            acc[q * 4 + 3] += sext_byte<3>(xs[q]) * mlt;
+          }
         }
         uint32_t packed[4];
 #pragma unroll
@@ -420,6 +431,12 @@ int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw
   }
   a.add_shift = add ? add->add_shift : 0; a.add_zp = add ? add->zp_out : 0;
   a.add_lo = add ? add->act_lo : 0; a.add_hi = add ? add->act_hi : 0;
+  {
+    long long init = add ? (1LL << (add->add_shift > 0 ? add->add_shift - 1 : 0)) : 0;
+    for (int i = 0; add && i < add->n_in; ++i) init -= (long long)add->zp_in[i] * add->add_mult[i];
+    if (init > INT32_MAX || init < INT32_MIN) return VBT_OK;      // cannot happen for int8 zero points
+    a.add_init = (int)init;
+  }
   a.B = B; a.H = dw.h_in; a.W = dw.w_in; a.c_p = dw.cout_p;
   a.groups = dw.cout_p / 16; a.pairs = (a.groups + 1) / 2; a.kch_pad = a.pairs * 2;
   a.wdiag = reinterpret_cast<const int8_t*>(m->dev_data + dw.lut_off);
@@ -440,15 +457,38 @@ int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw
   int max_tiles = kMaxTiles;
   while (max_tiles > 1 && std::max(a.pairs * 32, a.cout_p) * max_tiles > 256) --max_tiles;
   if (std::max(a.pairs * 32, a.cout_p) * max_tiles > 512) return VBT_OK;
-  // the most tiles per CTA (least halo recomputation) that still gives the GPU kMinCtas CTAs
-  static const int min_ctas = [] { const char* e = getenv("VBT_NODE_MIN_CTAS"); return e ? atoi(e) : 296; }();
+  // Tile choice: per candidate tile count, estimate waves x per-CTA work (window positions the fill
+  // has to produce, halo included, plus a fixed cost for the prologue / MMA / epilogue chain) and
+  // keep the cheapest.  A grid a few CTAs over one wave costs a whole extra wave (measured: the
+  // 40x40 nodes at 320 CTAs on 296 slots ran 2x longer than at 256).
   static const int cap_tiles = [] { const char* e = getenv("VBT_NODE_MT"); return e ? atoi(e) : kMaxTiles; }();
+  static const int fixed_cost = [] { const char* e = getenv("VBT_NODE_FIXED"); return e ? atoi(e) : 400; }();
   max_tiles = std::min(max_tiles, std::max(cap_tiles, 1));
-  for (int nt = max_tiles; nt >= 1; --nt) {
-    a.TH = std::max(1, std::min(a.H, nt * 128 / a.PW));
-    a.n_mt = (a.TH * a.PW + 127) / 128;
-    if (a.n_mt > max_tiles) continue;
-    if ((long long)B * ((a.H + a.TH - 1) / a.TH) >= min_ctas) break;
+  {
+    long long best = -1;
+    int best_th = 0, best_mt = 0;
+    for (int nt = max_tiles; nt >= 1; --nt) {
+      const int th = std::max(1, std::min(a.H, nt * 128 / a.PW));
+      const int n_mt = (th * a.PW + 127) / 128;
+      if (n_mt > max_tiles) continue;
+      const int bands = (a.H + th - 1) / th;
+      const int cols_c = std::max(a.pairs * 32, a.cout_p) * n_mt;
+      int cols_p = 32;
+      while (cols_p < cols_c) cols_p <<= 1;
+      const int mid_pl = (pw.pw_dtype == 1) ? 2 * a.groups : a.kch_pad;
+      const int plane = std::max(n_mt * 128 + 2 * a.PW + 2 + 8, (th + 2) * a.PW);
+      size_t sm = (size_t)a.kch_pad * plane * 16 + (size_t)mid_pl * n_mt * 2048 + (size_t)a.pairs * 9 * 1024 +
+                  (size_t)a.cout_p * mid_pl * 16;
+      if (sm > 200 * 1024) continue;
+      sm = std::max(sm, (size_t)228 * 1024 / (512 / cols_p + 1));
+      const int per_sm = std::max(1, std::min((int)(227 * 1024 / (sm + 2304)), 512 / cols_p));
+      const long long slots = 148LL * per_sm;
+      const long long waves = ((long long)B * bands + slots - 1) / slots;
+      const long long cost = waves * ((long long)(th + 2) * a.PW * (add ? 1 + a.n_in : 1) + fixed_cost);
+      if (best < 0 || cost < best) { best = cost; best_th = th; best_mt = n_mt; }
+    }
+    if (best < 0) return VBT_OK;
+    a.TH = best_th; a.n_mt = best_mt;
   }
   if (a.n_mt > max_tiles) return VBT_OK;
   a.n_bands = (a.H + a.TH - 1) / a.TH;

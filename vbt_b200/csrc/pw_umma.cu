@@ -92,7 +92,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
-template <bool HAS_RES>
+template <bool HAS_RES, bool FAST>
 __global__ void __launch_bounds__(NT) pw_umma_kernel(PwUmmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar;
@@ -224,8 +224,8 @@ __global__ void __launch_bounds__(NT) pw_umma_kernel(PwUmmaArgs a) {
       const int4 bq = *reinterpret_cast<const int4*>(sBias + c0 + q * 4);
       const float4 mq = *reinterpret_cast<const float4*>(sMult + c0 + q * 4);
       if (!HAS_RES) {
-        packed[q] = a.rq.pack4((int)v[q * 4 + 0] + bq.x, (int)v[q * 4 + 1] + bq.y, (int)v[q * 4 + 2] + bq.z,
-                               (int)v[q * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
+        packed[q] = a.rq.pack4t<FAST>((int)v[q * 4 + 0] + bq.x, (int)v[q * 4 + 1] + bq.y, (int)v[q * 4 + 2] + bq.z,
+                                      (int)v[q * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
       } else {
         const int bs[4] = {bq.x, bq.y, bq.z, bq.w};
         const float ms[4] = {mq.x, mq.y, mq.z, mq.w};
@@ -324,14 +324,16 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   smem = std::max(smem, (size_t)228 * 1024 / (cap_ctas + 1));
   static bool attr_set = false;
   if (!attr_set) {
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(pw_umma_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (smem > 200 * 1024) return VBT_OK;
   dim3 grid((unsigned)((a.M + TILE_M - 1) / TILE_M), (unsigned)((op.cout_p + a.nc - 1) / a.nc));
-  if (has_res) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<true>, grid, dim3(NT), smem, st, a));
-  else VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false>, grid, dim3(NT), smem, st, a));
+  if (has_res) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<true, false>, grid, dim3(NT), smem, st, a));
+  else if (a.rq.fast) VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false, true>, grid, dim3(NT), smem, st, a));
+  else VBT_CHECK_CUDA(launch_pdl(pw_umma_kernel<false, false>, grid, dim3(NT), smem, st, a));
   *taken = true;
   return VBT_OK;
 }

@@ -44,6 +44,11 @@ struct Requant {
   // is added afterwards, in integers, so ties still go to the even multiple of the output step).
   __device__ __forceinline__ uint32_t pack4(int a0, int a1, int a2, int a3, float m0, float m1, float m2,
                                             float m3) const;
+  // the same with the choice of path made at compile time (kernels templated on it: no branch,
+  // no divergence bookkeeping around every group of four channels)
+  template <bool FAST>
+  __device__ __forceinline__ uint32_t pack4t(int a0, int a1, int a2, int a3, float m0, float m1, float m2,
+                                             float m3) const;
 };
 
 // four values already inside [-128, 127] -> one little-endian word of int8
@@ -59,7 +64,13 @@ namespace vbt {
 
 __device__ __forceinline__ uint32_t Requant::pack4(int a0, int a1, int a2, int a3, float m0, float m1,
                                                    float m2, float m3) const {
-  if (!fast) return pack4_s8((*this)(a0, m0), (*this)(a1, m1), (*this)(a2, m2), (*this)(a3, m3));
+  return fast ? pack4t<true>(a0, a1, a2, a3, m0, m1, m2, m3) : pack4t<false>(a0, a1, a2, a3, m0, m1, m2, m3);
+}
+
+template <bool FAST>
+__device__ __forceinline__ uint32_t Requant::pack4t(int a0, int a1, int a2, int a3, float m0, float m1,
+                                                    float m2, float m3) const {
+  if (!FAST) return pack4_s8((*this)(a0, m0), (*this)(a1, m1), (*this)(a2, m2), (*this)(a3, m3));
   // scalar multiplies + packed adds: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2 even with
   // --fmad=false, which would round once instead of twice
   const float p0 = __fmul_rn(__int2float_rn(a0), m0), p1 = __fmul_rn(__int2float_rn(a1), m1);
