@@ -340,7 +340,9 @@ def main():
         if plan[i] > 1:
             run = g.ops[i:i + plan[i]]
             name = 'node_fused'
-            first_in = sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c for t in run[0].inputs)
+            produced = {o.out for o in run}
+            first_in = sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c
+                           for o in run for t in o.inputs if t not in produced)
             last = run[-1]
             t_in = g.tensors[last.inputs[0]]
             out_el = (g.tensors[last.out].h * g.tensors[last.out].w * g.tensors[last.out].c) if last.out >= 0 \

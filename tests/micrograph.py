@@ -102,11 +102,13 @@ def head_graph(h, w, c, cout, act=True, seed=0, out_kind=0):
     return g
 
 
-def node_graph(h, w, c, n_in=3, seed=0, odd=False):
+def node_graph(h, w, c, n_in=3, seed=0, odd=False, tree=False):
     """A BiFPN node on a pyramid built from the input: input [2h(-1), 2w(-1)] -> DW s2 -> p1
     [h, w] -> DW s2 -> p2; then ADD(max-pooled input, p1, up-sampled p2) -> ReLU6 -> DW3x3 ->
     PW(c->c), the triple csrc/node_umma.cu runs as one kernel.  n_in = 2 drops the max-pooled
-    input.  odd: the input is (2h-1, 2w-1), the 5 -> 3 / 7 -> 4 pooling case."""
+    input.  odd: the input is (2h-1, 2w-1), the 5 -> 3 / 7 -> 4 pooling case.  tree (n_in = 3):
+    the sum as the exported graphs hold it, ADD(ADD(pooled input, p1), up-sampled p2), the inner
+    ADD with its own output quantisation and no activation."""
     rng = np.random.default_rng(seed)
     g = _empty_graph(2 * h - (1 if odd else 0), 2 * w - (1 if odd else 0), c, 4)
     g.S = g.tensors[g.input].h
@@ -116,6 +118,15 @@ def node_graph(h, w, c, n_in=3, seed=0, odd=False):
     p2 = g._dw(p1, 3, 2, False, 'p2')
     _set_dw(rng, g, g.ops[-1], -13, 21, False)
     xs = [g.input, p1, p2] if n_in == 3 else [p1, p2]
+    if tree:
+        assert n_in == 3
+        t0 = g._fuse(xs[:2], (h, w), 'n.sum0', act=False)
+        op0 = g.ops[-1]
+        op0.q['zp_in'] = [g.tensors[x].zp for x in xs[:2]]
+        op0.q['zp_out'], op0.q['act_lo'], op0.q['act_hi'] = 9, -128, 127
+        op0.q['add_mult'], op0.q['add_shift'] = [int(0.37 * (1 << 20)), int(0.58 * (1 << 20))], 20
+        g.tensors[t0].zp = 9
+        xs, n_in = [t0, xs[2]], 2
     f = g._fuse(xs, (h, w), 'n.sum')
     op = g.ops[-1]
     zp_out = -128

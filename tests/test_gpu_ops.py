@@ -194,3 +194,14 @@ def test_fused_head_stage_bf16(h, w, c, cout, kind):
         assert np.array_equal(got[-2], box)
     else:
         assert np.array_equal(got[g.ops[-1].out][0].astype(np.int16), want[g.ops[-1].out])
+
+
+@pytest.mark.parametrize('h,w,c,odd,B', [(3, 3, 64, True, 4), (5, 5, 64, False, 3), (20, 20, 64, False, 2),
+                                          (40, 40, 64, False, 1), (12, 12, 88, False, 2), (7, 7, 112, True, 2),
+                                          (28, 28, 112, False, 1)])
+def test_fused_bifpn_node_with_add_tree(h, w, c, odd, B):
+    """ADD(ADD(a, b), c) -> DW -> PW: four ops, one kernel; the inner sum is requantised to its own
+    int8 tensor (and clamped) before the outer sum uses it."""
+    g = MG.node_graph(h, w, c, n_in=3, seed=h * 10 + c + 1, odd=odd, tree=True)
+    check(g, B)
+    assert list(MG.run_gpu.last_plan)[-4:] == [4, 0, 0, 0]

@@ -130,28 +130,40 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
     };
     // one kernel's CTAs write the run's output while others still read its inputs: the two
     // must not share workspace memory (effdet.plan_workspace keeps them apart)
-    auto disjoint = [&](const OpRecord& first, const OpRecord& last) {
-      if (last.out < 0) return true;
+    auto overlaps = [&](int tin, const OpRecord& last) {
+      if (last.out < 0 || tin < 0) return false;
       const TensorRecord& to = m->tensors[last.out];
+      const TensorRecord& ti = m->tensors[tin];
+      if (ti.ws_offset < 0) return false;               // the model input: caller's buffer
       const int64_t o0 = to.ws_offset, o1 = o0 + (int64_t)to.h * to.w * to.c_p;
-      for (int i = 0; i < first.n_in; ++i) {
-        if (first.in[i] < 0) continue;
-        const TensorRecord& ti = m->tensors[first.in[i]];
-        if (ti.ws_offset < 0) continue;               // the model input: caller's buffer
-        const int64_t i0 = ti.ws_offset, i1 = i0 + (int64_t)ti.h * ti.w * ti.c_p;
-        if (o0 < i1 && i0 < o1) return false;
-      }
+      const int64_t i0 = ti.ws_offset, i1 = i0 + (int64_t)ti.h * ti.w * ti.c_p;
+      return o0 < i1 && i0 < o1;
+    };
+    auto disjoint = [&](int first, int last) {           // no external input of ops[first..last) aliases the output
+      for (int j = first; j < last; ++j)
+        for (int i = 0; i < m->ops[j].n_in; ++i)
+          if (overlaps(m->ops[j].in[i], m->ops[last])) return false;
       return true;
+    };
+    auto add_dw_pw = [&](int i) {                        // ops[i] = ADD feeding DW3x3 -> PW
+      const OpRecord& o = m->ops[i];
+      return o.type == OP_ADD && i + 2 < n && o.out >= 0 && readers[o.out] == 1 &&
+             m->ops[i + 1].in[0] == o.out && m->ops[i + 1].branch == o.branch && dw_ok(m->ops[i + 1]) &&
+             pw_ok(m->ops[i + 2], m->ops[i + 1]);
     };
     m->fuse.assign(n, 1);
     for (int i = 0; i < n;) {
       const OpRecord& o = m->ops[i];
-      if (max_hw > 0 && o.type == OP_ADD && i + 2 < n && o.out >= 0 && readers[o.out] == 1 &&
-          m->ops[i + 1].in[0] == o.out && m->ops[i + 1].branch == o.branch && dw_ok(m->ops[i + 1]) &&
-          pw_ok(m->ops[i + 2], m->ops[i + 1]) && disjoint(o, m->ops[i + 2])) {
+      if (max_hw > 0 && o.type == OP_ADD && o.n_in == 2 && o.out >= 0 && readers[o.out] == 1 && i + 3 < n &&
+          m->ops[i + 1].type == OP_ADD && m->ops[i + 1].n_in == 2 && m->ops[i + 1].branch == o.branch &&
+          (m->ops[i + 1].in[0] == o.out || m->ops[i + 1].in[1] == o.out) && add_dw_pw(i + 1) &&
+          disjoint(i, i + 3)) {
+        m->fuse[i] = 4; m->fuse[i + 1] = m->fuse[i + 2] = m->fuse[i + 3] = 0;
+        i += 4;
+      } else if (max_hw > 0 && add_dw_pw(i) && disjoint(i, i + 2)) {
         m->fuse[i] = 3; m->fuse[i + 1] = m->fuse[i + 2] = 0;
         i += 3;
-      } else if (max_hw > 0 && i + 1 < n && dw_ok(o) && pw_ok(m->ops[i + 1], o) && disjoint(o, m->ops[i + 1])) {
+      } else if (max_hw > 0 && i + 1 < n && dw_ok(o) && pw_ok(m->ops[i + 1], o) && disjoint(i, i + 1)) {
         m->fuse[i] = 2; m->fuse[i + 1] = 0;
         i += 2;
       } else {

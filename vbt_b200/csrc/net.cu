@@ -24,8 +24,8 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
                    int8_t* out, long long out_batch_stride, int B, cudaStream_t st, bool* taken);
 int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int8_t* out, int B,
                    cudaStream_t st, bool* taken);
-int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw, const OpRecord& pw,
-                     const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
+int launch_node_umma(const vbt_model* m, const OpRecord* add0, const OpRecord* add, const OpRecord& dw,
+                     const OpRecord& pw, const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
                      cudaStream_t st, bool* taken);
 }
 
@@ -511,20 +511,27 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
     // fused [ADD ->] DW3x3 -> PW group: one kernel; falls through to the single ops if declined
     int covered = 1;
     if (m->fuse[oi] > 1) {
-      const int glen = m->fuse[oi];
-      const OpRecord* add = glen == 3 ? &op : nullptr;
+      const int glen = m->fuse[oi];                        // 2: DW PW; 3: ADD DW PW; 4: ADD ADD DW PW
+      const OpRecord* add0 = glen == 4 ? &op : nullptr;
+      const OpRecord* add = glen >= 3 ? &m->ops[oi + glen - 3] : nullptr;
       const OpRecord& dwop = m->ops[oi + glen - 2];
       const OpRecord& pwop = m->ops[oi + glen - 1];
       const int8_t* ins[3] = {nullptr, nullptr, nullptr};
-      if (add) for (int i = 0; i < add->n_in; ++i) ins[i] = tensor_ptr(add->in[i]);
-      else ins[0] = tensor_ptr(dwop.in[0]);
+      if (add0) {
+        ins[0] = tensor_ptr(add0->in[0]); ins[1] = tensor_ptr(add0->in[1]);
+        ins[2] = tensor_ptr(add->in[0] == add0->out ? add->in[1] : add->in[0]);
+      } else if (add) {
+        for (int i = 0; i < add->n_in; ++i) ins[i] = tensor_ptr(add->in[i]);
+      } else {
+        ins[0] = tensor_ptr(dwop.in[0]);
+      }
       int8_t* out;
       long long obs;
       if (pwop.out_kind == 0) { out = tensor_ptr(pwop.out); obs = (long long)pwop.h_out * pwop.w_out * pwop.cout_p; }
       else if (pwop.out_kind == 1) { out = dev_out_cls; obs = Np * m->hdr.n_classes; }
       else { out = dev_out_box; obs = Np * 4; }
       bool node_taken = false;
-      if (int rc = launch_node_umma(m, add, dwop, pwop, ins, out, obs, B, st, &node_taken)) return rc;
+      if (int rc = launch_node_umma(m, add0, add, dwop, pwop, ins, out, obs, B, st, &node_taken)) return rc;
       if (node_taken) covered = glen;
     }
     if (covered == 1) {

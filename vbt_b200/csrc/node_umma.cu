@@ -11,7 +11,9 @@
 //      shared-memory planes, one per 16-channel group, [position][16 B] with
 //      position = y * PW + x.  Either a copy of one tensor (heads) or the BiFPN fusion
 //      computed on the fly: nearest-neighbour up-sampling / 3x3 s2 max-pool down-sampling of
-//      up to three inputs, integer rescale, sum, ReLU6 clamp -- the arithmetic of add_kernel;
+//      up to three inputs, integer rescale, sum, ReLU6 clamp -- the arithmetic of add_kernel.
+//      A 3-input sum arrives as the exported graphs hold it, ADD(ADD(a, b), c): the inner sum is
+//      requantised to its own int8 tensor (in registers) before the outer one uses it;
 //   2. depthwise: as dw_umma.cu -- per 128-position tile and channel-group pair, nine
 //      tcgen05.mma with block-diagonal weights whose A descriptors are shifted views of the
 //      planes; accumulators in TMEM; the epilogue requantises into a second set of planes;
@@ -41,6 +43,8 @@ struct NodeArgs {
   int in_h[3], in_w[3], resample[3], zp_in[3], add_mult[3];
   int add_shift, add_zp, add_lo, add_hi;
   int add_init;                    // rounding constant minus sum_i zp_i * mult_i (the zero points folded out)
+  // inner ADD of a two-level sum ADD(ADD(in[0], in[1]), in[2]); pre_n = 0: single-level sum
+  int pre_n, pre_mult[2], pre_init, pre_shift, pre_zp, pre_lo, pre_hi, pre_out_mult;
   // geometry (depthwise 3x3 stride 1: output size = input size)
   int B, H, W, c_p, groups, pairs, kch_pad;
   // depthwise
@@ -245,7 +249,28 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
         int acc[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) acc[j] = a.add_init;
-        for (int n = 0; n < a.n_in; ++n) {
+        if (a.pre_n) {                                 // inner sum -> its own int8 value -> outer sum
+          int acc0[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc0[j] = a.pre_init;
+          for (int n = 0; n < 2; ++n) {
+            const uint4 v = fetch_resampled(a.in[n], b, iy, ix, a.H, a.W, a.in_h[n], a.in_w[n], a.resample[n],
+                                            a.c_p, g * 16);
+            const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
+            const int mlt = a.pre_mult[n];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              acc0[q * 4 + 0] += sext_byte<0>(xs[q]) * mlt;
+              acc0[q * 4 + 1] += sext_byte<1>(xs[q]) * mlt;
+              acc0[q * 4 + 2] += sext_byte<2>(xs[q]) * mlt;
+              acc0[q * 4 + 3] += sext_byte<3>(xs[q]) * mlt;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            acc[j] += clampi((acc0[j] >> a.pre_shift) + a.pre_zp, a.pre_lo, a.pre_hi) * a.pre_out_mult;
+        }
+        for (int n = a.pre_n; n < a.n_in; ++n) {
           const uint4 v = fetch_resampled(a.in[n], b, iy, ix, a.H, a.W, a.in_h[n], a.in_w[n], a.resample[n],
                                           a.c_p, g * 16);
           const uint32_t xs[4] = {v.x, v.y, v.z, v.w};
@@ -416,27 +441,54 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
 namespace vbt {
 
 // ops[i .. i+n): [ADD] DW PW.  Returns VBT_OK and *taken = true when the fused kernel took them.
-int launch_node_umma(const vbt_model* m, const OpRecord* add, const OpRecord& dw, const OpRecord& pw,
-                     const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
+int launch_node_umma(const vbt_model* m, const OpRecord* add0, const OpRecord* add, const OpRecord& dw,
+                     const OpRecord& pw, const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
                      cudaStream_t st, bool* taken) {
+  // add0 != null: ADD(add0(in[0], in[1]), in[2]); `pos` = which operand of `add` is add0's output
   *taken = false;
   NodeArgs a;
-  a.n_in = add ? add->n_in : 1;
   a.fused_add = add != nullptr;
+  a.pre_n = 0;
   for (int i = 0; i < 3; ++i) {
     a.in[i] = in[i];
-    a.in_h[i] = add ? add->in_h[i] : 0; a.in_w[i] = add ? add->in_w[i] : 0;
-    a.resample[i] = add ? add->resample[i] : 0; a.zp_in[i] = add ? add->zp_in[i] : 0;
-    a.add_mult[i] = add ? add->add_mult[i] : 0;
+    a.in_h[i] = a.in_w[i] = a.resample[i] = a.zp_in[i] = a.add_mult[i] = 0;
   }
+  a.pre_mult[0] = a.pre_mult[1] = a.pre_init = a.pre_shift = a.pre_zp = a.pre_lo = a.pre_hi = a.pre_out_mult = 0;
+  long long init = add ? (1LL << (add->add_shift > 0 ? add->add_shift - 1 : 0)) : 0;
+  if (add && !add0) {
+    a.n_in = add->n_in;
+    for (int i = 0; i < add->n_in; ++i) {
+      a.in_h[i] = add->in_h[i]; a.in_w[i] = add->in_w[i]; a.resample[i] = add->resample[i];
+      a.zp_in[i] = add->zp_in[i]; a.add_mult[i] = add->add_mult[i];
+      init -= (long long)add->zp_in[i] * add->add_mult[i];
+    }
+  } else if (add && add0) {
+    if (add0->n_in != 2 || add->n_in != 2) return VBT_OK;
+    const int pos = add->in[0] == add0->out ? 0 : 1;
+    if (add->in[pos] != add0->out || add->resample[pos] != RS_NONE) return VBT_OK;
+    a.n_in = 3; a.pre_n = 2;
+    long long init0 = 1LL << (add0->add_shift > 0 ? add0->add_shift - 1 : 0);
+    for (int i = 0; i < 2; ++i) {
+      a.in_h[i] = add0->in_h[i]; a.in_w[i] = add0->in_w[i]; a.resample[i] = add0->resample[i];
+      a.pre_mult[i] = add0->add_mult[i];
+      init0 -= (long long)add0->zp_in[i] * add0->add_mult[i];
+    }
+    if (init0 > INT32_MAX || init0 < INT32_MIN) return VBT_OK;
+    a.pre_init = (int)init0; a.pre_shift = add0->add_shift; a.pre_zp = add0->zp_out;
+    a.pre_lo = add0->act_lo; a.pre_hi = add0->act_hi;
+    a.pre_out_mult = add->add_mult[pos];
+    init -= (long long)add->zp_in[pos] * add->add_mult[pos];
+    const int o = 1 - pos;
+    a.in_h[2] = add->in_h[o]; a.in_w[2] = add->in_w[o]; a.resample[2] = add->resample[o];
+    a.add_mult[2] = add->add_mult[o];
+    init -= (long long)add->zp_in[o] * add->add_mult[o];
+  } else {
+    a.n_in = 1;
+  }
+  if (init > INT32_MAX || init < INT32_MIN) return VBT_OK;            // cannot happen for int8 zero points
+  a.add_init = (int)init;
   a.add_shift = add ? add->add_shift : 0; a.add_zp = add ? add->zp_out : 0;
   a.add_lo = add ? add->act_lo : 0; a.add_hi = add ? add->act_hi : 0;
-  {
-    long long init = add ? (1LL << (add->add_shift > 0 ? add->add_shift - 1 : 0)) : 0;
-    for (int i = 0; add && i < add->n_in; ++i) init -= (long long)add->zp_in[i] * add->add_mult[i];
-    if (init > INT32_MAX || init < INT32_MIN) return VBT_OK;      // cannot happen for int8 zero points
-    a.add_init = (int)init;
-  }
   a.B = B; a.H = dw.h_in; a.W = dw.w_in; a.c_p = dw.cout_p;
   a.groups = dw.cout_p / 16; a.pairs = (a.groups + 1) / 2; a.kch_pad = a.pairs * 2;
   a.wdiag = reinterpret_cast<const int8_t*>(m->dev_data + dw.lut_off);

@@ -470,7 +470,7 @@ def quantize(g: Graph, calib_frames):
 
 
 def fused_run_end(g):
-    """run_end[i] = index of the last op of the [ADD ->] DW3x3 s1 -> PW run op i may be executed
+    """run_end[i] = index of the last op of the [[ADD ->] ADD ->] DW3x3 s1 -> PW run op i may be executed
     in as one kernel (vbt_model_create's launch plan, csrc/model.cu), i itself otherwise.  A
     superset of what the library fuses is fine: it only delays memory reuse."""
     n = len(g.ops)
@@ -489,11 +489,20 @@ def fused_run_end(g):
                 t.c_p <= 128 and max(t.h, t.w) <= FUSE_MAX_HW and pad16(g.out_channels(p)) <= 128 and
                 p.type == OP_PW and p.inputs == [d.out] and p.residual < 0 and p.branch == d.branch)
 
+    def add_dw_pw(i):
+        o = g.ops[i]
+        return (o.type == OP_ADD and readers.get(o.out, 0) == 1 and dw_pw(i + 1) and
+                g.ops[i + 1].inputs == [o.out] and g.ops[i + 1].branch == o.branch)
+
     i = 0
     while i < n:
         o = g.ops[i]
-        if o.type == OP_ADD and readers.get(o.out, 0) == 1 and dw_pw(i + 1) and \
-                g.ops[i + 1].inputs == [o.out] and g.ops[i + 1].branch == o.branch:
+        if (o.type == OP_ADD and len(o.inputs) == 2 and readers.get(o.out, 0) == 1 and i + 1 < n and
+                g.ops[i + 1].type == OP_ADD and len(g.ops[i + 1].inputs) == 2 and o.out in g.ops[i + 1].inputs and
+                g.ops[i + 1].branch == o.branch and add_dw_pw(i + 1)):
+            end[i] = end[i + 1] = end[i + 2] = end[i + 3] = i + 3
+            i += 4
+        elif add_dw_pw(i):
             end[i] = end[i + 1] = end[i + 2] = i + 2
             i += 3
         elif dw_pw(i):
