@@ -190,3 +190,53 @@ def test_config3_lite2_bf16_heads_equal_int8_heads():
     imgs = OR.preprocess_batch(frames[pick], g8.S, swap_rb=True)
     want_cls, want_box, _ = OE.run(g16, imgs)
     assert np.array_equal(cls16[pick], want_cls) and np.array_equal(box16[pick], want_box)
+
+
+def test_one_video_in_frame_chunks_equals_one_pass():
+    """shard.track_video_chunks: detection on contiguous frame chunks (here three chunks run one
+    after the other on this GPU, then concatenated as the gather would), tracker + velocity over
+    the whole table -- rows and phases equal the ordinary one-pass pipeline and the oracle chain.
+    The collective itself is covered on CPU by tests/test_shard_gloo.py."""
+    import torch
+    from vbt_b200 import shard
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    g = graph('lite0')
+    det = Detector(g, max_batch=8)
+    n, thr, fps = 37, 0.3, 30.0
+    frames_np = synthetic_frames(n, 135, 240, seed=31)
+    frames = torch.as_tensor(frames_np, device='cuda')
+    video = {'fps': fps, 'frames': frames}
+    one = shard.track_video_chunks(video, det, detection_threshold=thr, row_cap=4096)     # world of 1
+    want = oracle_rows(g, frames_np, fps, thr)
+    assert len(want) > 0 and np.array_equal(one['rows'], want)
+    for stride, world in ((1, 3), (2, 2)):
+        keep = torch.arange(stride, n + 1, stride, dtype=torch.int32)
+        loaded = []
+
+        def load(a, b):
+            loaded.append((a, b))
+            return frames[a:b]
+        vid = {'fps': fps, 'n_frames': n, 'load': load}
+        parts = []
+        for lo, hi in shard.chunk_bounds(len(keep), world):
+            pipe = VideoPipeline(det, fps, thr, row_cap=4096)
+            parts.append(shard.detect_chunk(pipe, vid, keep[lo:hi], stride))
+        table = [torch.cat([p[i] for p in parts]) for i in range(3)]
+        assert table[2].cpu().tolist() == keep.tolist()
+        assert all(b - a <= 8 * stride for a, b in loaded)           # a rank only loads its own batches
+        pipe = VideoPipeline(det, fps, thr, row_cap=4096)
+        pipe.track_table(*table)
+        res = pipe.finish()
+        ref = VideoPipeline(det, fps, thr, row_cap=4096)
+        for s in range(0, len(keep), 8):
+            idx = keep[s:s + 8].long() - 1
+            ref.process(frames[idx.cuda()].contiguous(), keep[s:s + 8].cuda(), swap_rb=True)
+        r = ref.finish()
+        assert np.array_equal(res['rows'], r['rows'])
+        if stride == 1:
+            assert np.array_equal(res['rows'], want)
+        assert sorted(res['phases']) == sorted(r['phases'])
+        for tid in res['phases']:
+            assert [(p.time_start, p.time_end, p.rom, p.type) for p in res['phases'][tid]] == \
+                   [(p.time_start, p.time_end, p.rom, p.type) for p in r['phases'][tid]]

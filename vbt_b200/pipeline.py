@@ -108,10 +108,13 @@ class VideoPipeline:
             s.wait_stream(cur)
         self.side.wait_stream(cur)
 
-    def process(self, frames, frame_numbers, swap_rb=True):
+    def process(self, frames, frame_numbers, swap_rb=True, track=True):
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
         tensor [n] with the 1-based frame_count of each (track.py:161).  Both must be ready on
-        the current stream; `self.input_consumed` is recorded once K1 has read `frames`."""
+        the current stream; `self.input_consumed` is recorded once K1 has read `frames`.
+        track=False: detection only (K1 -> network -> K6 -> pack); the packed tracker inputs of
+        the batch are kept on the device for `detection_table()` (frame-chunk sharding of one
+        long video, shard.track_video_chunks: the tracker runs later, on the gathered table)."""
         t = self.torch
         n = frames.shape[0]
         lane = self.batches % self.active_lanes
@@ -156,6 +159,14 @@ class VideoPipeline:
             self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
             self.n_frames[k].fill_(n)
             self._mark(marks)
+            if not track:
+                if not hasattr(self, '_table'):
+                    self._table = []
+                self._table.append((self.dets[k, 0, :n].clone(), self.det_count[k, 0, :n].clone(),
+                                    self.frame_no[k, 0, :n].clone()))
+                self.slot_free[k].record(ds)
+                self.frames_done += n
+                return
             self.det_ready[k].record(ds)
         side = self.side
         side.wait_event(self.det_ready[k])             # batches reach the side stream in order
@@ -173,6 +184,45 @@ class VideoPipeline:
         if marks is not None:
             self.stage_events.append(marks)
         self.frames_done += n
+
+    def detection_table(self):
+        """(dets f64 [n,25,6], counts i32 [n], frame numbers i32 [n]) of every batch processed with
+        track=False since the last call, in order, on the device."""
+        t = self.torch
+        self._sync_streams()
+        parts, self._table = getattr(self, '_table', []), []
+        D = self.det.max_det
+        if not parts:
+            return (t.zeros((0, D, 6), dtype=t.float64, device='cuda'), t.zeros(0, dtype=t.int32, device='cuda'),
+                    t.zeros(0, dtype=t.int32, device='cuda'))
+        return tuple(t.cat([p[i] for p in parts]) for i in range(3))
+
+    def track_table(self, dets, counts, frame_numbers):
+        """K7 + K8 over a detection table (the output of `detection_table`, possibly gathered from
+        several ranks), in frame order, `max_batch` frames per tracker call."""
+        t = self.torch
+        self._sync_streams()
+        side = self.side
+        side.wait_stream(t.cuda.current_stream())
+        n_all = int(dets.shape[0])
+        with t.cuda.stream(side):
+            for s in range(0, n_all, self.F):
+                n = min(self.F, n_all - s)
+                k = self.batches % self.N_SLOTS
+                self.batches += 1
+                self.dets[k, 0, :n].copy_(dets[s:s + n])
+                self.det_count[k, 0, :n].copy_(counts[s:s + n])
+                self.frame_no[k, 0, :n].copy_(frame_numbers[s:s + n])
+                self.n_frames[k].fill_(n)
+                self.tracker.update(self.dets[k], self.det_count[k], self.frame_no[k], self.d_fps,
+                                    self.n_frames[k], stream=side)
+                self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
+                                  self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
+                                  self.plate_diameter, self.diff_threshold, self.min_distance,
+                                  smooth=True, finish=False)
+                self.slot_free[k].record(side)
+        for x in (dets, counts, frame_numbers):
+            x.record_stream(side)
 
     def finish(self):
         """End of video: run end_processing() on every lane, bring results to the host.

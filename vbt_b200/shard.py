@@ -1,4 +1,5 @@
-"""Multi-GPU sharding of the hot path: whole videos per rank, one gather at the end.
+"""Multi-GPU sharding of the hot path: whole videos per rank (or, for one long video, contiguous
+frame chunks per rank), one gather at the end.
 
 The reference processes its sources one after the other, each with a fresh interpreter
 and a fresh tracker (track.py:88-101,157) and writes one pickle per video
@@ -11,6 +12,12 @@ gloo in the CPU tests):
 * ``gather_row_tables`` -- the ONE exchange step: all_gather of per-video row counts,
                            then all_gather of each rank's row tables packed into one
                            padded [rows, 8] float64 buffer.  Never called per frame.
+* ``track_video_chunks`` -- ONE long video over all ranks: detection (K1-K6, per-frame
+                           independent, ~98 % of the work) on contiguous frame chunks, one gather
+                           of the packed detection tables (1.2 kB per frame), then the sequential
+                           tracker / velocity recurrence (K7, K8) over the whole table on rank 0.
+                           No tracker state crosses ranks, so no hand-off is needed and the result
+                           is the 1-rank result byte for byte (second scheme).
 """
 from __future__ import annotations
 
@@ -110,3 +117,87 @@ def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank
         phases[vi] = res['phases']
     tables = gather_row_tables(local, len(videos), group=group)
     return tables, phases
+
+
+def chunk_bounds(n_items, world_size):
+    """[(first, last_exclusive)] per rank: contiguous, balanced, earlier ranks take the remainder."""
+    base, rem = divmod(int(n_items), world_size)
+    out, at = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        out.append((at, at + n))
+        at += n
+    return out
+
+
+def gather_detection_tables(dets, counts, numbers, group=None):
+    """All ranks' detection tables concatenated in rank order (= frame order for contiguous
+    chunks): dets f64 [n,D,6], counts i32 [n], frame numbers i32 [n], torch tensors on the
+    collective's device.  Two collectives: the chunk lengths, then one padded payload per table."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return dets, counts, numbers
+    world = dist.get_world_size(group)
+    dev = dets.device
+    n = torch.tensor([dets.shape[0]], dtype=torch.int64, device=dev)
+    ns = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(ns, n, group=group)
+    ns = [int(x.item()) for x in ns]
+    pad = max(max(ns), 1)
+    D = dets.shape[1]
+    # one float64 payload: [pad, D*6 + 2] = detections, count, frame number (exact in float64)
+    payload = torch.zeros((pad, D * 6 + 2), dtype=torch.float64, device=dev)
+    m = dets.shape[0]
+    payload[:m, :D * 6] = dets.reshape(m, D * 6)
+    payload[:m, D * 6] = counts.to(torch.float64)
+    payload[:m, D * 6 + 1] = numbers.to(torch.float64)
+    gathered = [torch.empty_like(payload) for _ in range(world)]
+    dist.all_gather(gathered, payload, group=group)
+    full = torch.cat([g[:k] for g, k in zip(gathered, ns)])
+    return (full[:, :D * 6].reshape(-1, D, 6).contiguous(), full[:, D * 6].to(torch.int32),
+            full[:, D * 6 + 1].to(torch.int32))
+
+
+def track_video_chunks(video, detector, detection_threshold=0.5, frame_stride=1, rank=None, world=None,
+                       group=None, result_on_all_ranks=False, **pipe_kw):
+    """ONE video, its kept frames split into contiguous chunks across the ranks.
+
+    video: ``{'fps': float, 'frames': uint8 [N,H,W,3] tensor}`` or ``{'fps', 'n_frames', 'load':
+    callable(first, last_exclusive) -> uint8 [m,H,W,3]}`` (0-based source frame range), so that a
+    rank only ever decodes / holds its own chunk.  Returns the `VideoPipeline.finish()` dict on
+    rank 0 (on every rank with result_on_all_ranks), else None."""
+    import torch
+    import torch.distributed as dist
+    from .pipeline import VideoPipeline
+    if world is None:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+    n_src = int(video['n_frames']) if 'load' in video else int(video['frames'].shape[0])
+    keep = torch.arange(frame_stride, n_src + 1, frame_stride, dtype=torch.int32)   # 1-based (track.py:161,166)
+    lo, hi = chunk_bounds(len(keep), world)[rank]
+    pipe = VideoPipeline(detector, video['fps'], detection_threshold, **pipe_kw)
+    dets, counts, numbers = detect_chunk(pipe, video, keep[lo:hi], frame_stride)
+    dets, counts, numbers = gather_detection_tables(dets, counts, numbers, group=group)
+    if rank != 0 and not result_on_all_ranks:
+        return None
+    pipe.track_table(dets, counts, numbers)
+    return pipe.finish()
+
+
+def detect_chunk(pipe, video, keep, frame_stride=1):
+    """K1-K6 + pack over the kept frames `keep` (1-based frame numbers, int32 tensor) of one
+    video -> this chunk's detection table on the device."""
+    B = pipe.det.max_batch
+    numbers = keep.to('cuda')
+    for s in range(0, len(keep), B):
+        idx = keep[s:s + B].long() - 1
+        if 'load' in video:
+            chunk = video['load'](int(idx[0]), int(idx[-1]) + 1)
+            chunk = chunk[::frame_stride] if frame_stride > 1 else chunk
+        else:
+            frames = video['frames']
+            chunk = frames[idx[0]:idx[-1] + 1] if frame_stride == 1 else frames[idx.to(frames.device)]
+        pipe.process(chunk.contiguous(), numbers[s:s + B], swap_rb=True, track=False)
+    return pipe.detection_table()
