@@ -149,6 +149,12 @@ int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* de
                        const int32_t* dev_n_frames, int F, int max_det, double* dev_rows,
                        int32_t* dev_row_count, int row_cap, double* dev_last_out,
                        int32_t* dev_last_out_count, void* stream);
+/* Optional: from now on vbt_tracker_update also writes, for every appended row, the tracker
+ * output box and confidence the reference unpacks at track.py:190 for its overlay
+ * (draw_bounding_box, track.py:28-49): f64 [V,row_cap,VBT_ROW_DETAIL_COLS] = (xmin,ymin,xmax,ymax,
+ * score), same row index as `rows`.  NULL switches it off. */
+#define VBT_ROW_DETAIL_COLS 5
+int vbt_tracker_row_details(vbt_tracker* t, double* dev_row_details);
 /* status i32 [V]: 0 ok, VBT_ECAPACITY if tracks/rows overflowed.  Synchronises. */
 int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream);
 /* copies track.kf.x (7 doubles) + id + time_since_update of every live track of video

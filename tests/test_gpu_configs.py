@@ -240,3 +240,67 @@ def test_one_video_in_frame_chunks_equals_one_pass():
         for tid in res['phases']:
             assert [(p.time_start, p.time_end, p.rom, p.type) for p in res['phases'][tid]] == \
                    [(p.time_start, p.time_end, p.rom, p.type) for p in r['phases'][tid]]
+
+
+def test_track_cli_writes_the_annotated_video(tmp_path):
+    """--video_dir (track.py:152-154,241-242): one mp4v frame per processed frame that had a detection
+    >= threshold; the per-row overlay inputs (tracker output box + score, track.py:190) equal the
+    oracle tracker's return values; the written frames carry the white overlay."""
+    import cv2
+    from vbt_b200.interpreter import Interpreter
+    from vbt_b200.track import track
+    g = graph('lite0')
+    path = str(tmp_path / 'clip.avi')
+    frames = synthetic_frames(10, 240, 320, seed=6)
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*'MJPG'), 30.0, (320, 240))
+    for f in frames:
+        wr.write(f)
+    wr.release()
+    cap = cv2.VideoCapture(path)
+    decoded = []
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        decoded.append(f)
+    cap.release()
+    decoded = np.stack(decoded)
+    interp = Interpreter(model_path=g, num_threads=4)
+    thr = 0.3
+    out = str(tmp_path / 'clip.mp4')
+    data, res = track(path, interp, thr, video_path=out, frame_stride=1, batch=4, return_pipeline_result=True)
+    # overlay inputs vs the oracle: tracker.update()'s own (xmin,ymin,xmax,ymax,...,score) per emitted row
+    imgs = OR.preprocess_batch(decoded, g.S, swap_rb=True)
+    cls, box, _ = OE.run(g, imgs)
+    trk = oo.OCSortOracle(max_age=30, iou_threshold=0.1)
+    want, with_results = [], []
+    for b in range(len(decoded)):
+        ob, _, osc, cnt, _ = OP.detection_postprocess(cls[b], box[b], g.anchors(), g.box_scale, g.box_zp, min_score_q=-128)
+        d = OP.tracker_inputs(OP.detect_results(ob, osc, cnt, thr)).reshape(-1, 6)
+        if len(d) == 0:
+            continue
+        with_results.append(b + 1)
+        for row in trk.update(d):
+            want.append([row[0], row[1], row[2], row[3], row[6]])
+    assert res['frames_with_results'] == with_results and len(with_results) > 0
+    assert np.array_equal(res['details'], np.asarray(want, dtype=np.float64).reshape(-1, 5))
+    assert len(res['details']) == len(data['id']) > 0
+    # the file: frame count, size, and overlay pixels (mp4v is lossy: compare loosely)
+    cap = cv2.VideoCapture(out)
+    n_written = 0
+    first = None
+    while True:
+        ok, f = cap.read()
+        if not ok:
+            break
+        first = f if first is None else first
+        n_written += 1
+    cap.release()
+    assert n_written == len(with_results) and first.shape == (240, 320, 3)
+    t0 = min(data['time'])
+    r0 = [i for i, t in enumerate(data['time']) if t == t0][0]
+    xmin, ymin, xmax, ymax, _ = res['details'][r0]
+    x0, x1, y0 = max(int(xmin * 320), 0), min(int(xmax * 320), 319), int(ymin * 240)
+    if 2 <= y0 < 238 and x1 - x0 > 8:
+        edge = first[y0, x0 + 3:x1 - 3].astype(int)
+        assert edge.mean() > 200, 'the top edge of the first box should be (nearly) white'

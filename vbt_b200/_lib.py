@@ -57,6 +57,7 @@ PROTOTYPES = {
     'vbt_tracker_destroy': (None, [_P]),
     'vbt_tracker_reset': (_I, [_P, _P]),
     'vbt_tracker_update': (_I, [_P, _P, _P, _P, _P, _P, _I, _I, _P, _P, _I, _P, _P, _P]),
+    'vbt_tracker_row_details': (_I, [_P, _P]),
     'vbt_tracker_status': (_I, [_P, _P, _P]),
     'vbt_tracker_peek': (_I, [_P, _I, _P, _P]),
     'vbt_velocity_create': (_I, [_I, _I, _I, C.POINTER(_P)]),

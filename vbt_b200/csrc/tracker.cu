@@ -444,7 +444,8 @@ __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) 
 __global__ void __launch_bounds__(32) tracker_update_kernel(
     Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
     const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det, int max_tracks,
-    double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count) {
+    double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count,
+    double* row_details) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ Shared sh;
   const unsigned full = 0xffffffffu;
@@ -794,6 +795,10 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
             r[5] = dxy[1];
             r[6] = fabs(box[3] - box[1]);          // odt.py:32-40
             r[7] = fabs(box[2] - box[0]);          // odt.py:22-29
+            if (row_details) {                     // what track.py:190 unpacks for the overlay
+              double* d = row_details + ((size_t)v * row_cap + rc + pos) * VBT_ROW_DETAIL_COLS;
+              d[0] = box[0]; d[1] = box[1]; d[2] = box[2]; d[3] = box[3]; d[4] = cc[1];
+            }
           }
           if (last_out && last_frame && n_out + pos < max_det) {
             double* o = last_out + ((size_t)v * max_det + n_out + pos) * 9;
@@ -875,6 +880,7 @@ struct vbt_tracker {
   Video* videos;
   Trk* tracks;
   double* peek;      // [kMaxT*9 + 1]
+  double* row_details = nullptr;   // optional f64 [V,row_cap,5] next to the rows (vbt_tracker_row_details)
   int32_t* scratch;  // [max(V,1)]
 };
 
@@ -926,8 +932,15 @@ int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* de
               "vbt_tracker_update: F=%d max_det=%d (<=%d) row_cap=%d", F, max_det, kMaxD, row_cap);
   tracker_update_kernel<<<t->V, 32, shared_bytes(t->max_tracks), (cudaStream_t)stream>>>(
       t->videos, t->tracks, t->prm, dev_dets, dev_det_count, dev_frame_no, dev_fps, dev_n_frames,
-      F, max_det, t->max_tracks, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count);
+      F, max_det, t->max_tracks, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count,
+      t->row_details);
   VBT_LAUNCHED(1);
+  return VBT_OK;
+}
+
+int vbt_tracker_row_details(vbt_tracker* t, double* dev_row_details) {
+  VBT_REQUIRE(t, "vbt_tracker_row_details: null handle");
+  t->row_details = dev_row_details;
   return VBT_OK;
 }
 

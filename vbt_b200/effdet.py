@@ -381,8 +381,15 @@ def float_forward(g: Graph, frames_u8, record=None):
     return vals, outs
 
 
+def _coarse(x):
+    """Calibrated range end rounded to four significant digits: the float forward pass sums in a
+    thread-count dependent order, and a model built under torchrun (OMP_NUM_THREADS=1) must be the
+    model built anywhere else -- ranks compare results byte for byte."""
+    return float(f'{float(x):.4g}')
+
+
 def _qparams(lo, hi):
-    lo, hi = min(lo, 0.0), max(hi, 0.0)
+    lo, hi = min(_coarse(lo), 0.0), max(_coarse(hi), 0.0)
     if hi - lo < 1e-6:
         hi = lo + 1e-6
     scale = (hi - lo) / 255.0

@@ -33,7 +33,7 @@ class BatchedTracker:
 
     def __init__(self, n_videos=1, row_cap=1 << 16, det_thresh=0.2, max_age=30, min_hits=3,
                  iou_threshold=0.1, delta_t=3, inertia=0.2, vdc_uses_class_column=True,
-                 max_tracks=MAX_TRACKS):
+                 max_tracks=MAX_TRACKS, keep_details=False):
         self.torch = t = _lib.require_cuda()
         self.V, self.row_cap = n_videos, row_cap
         p = _params(det_thresh, max_age, min_hits, iou_threshold, delta_t, inertia,
@@ -43,6 +43,10 @@ class BatchedTracker:
         self.handle = h
         self.rows = t.zeros((n_videos, row_cap, _lib.ROW_COLS), dtype=t.float64, device='cuda')
         self.row_count = t.zeros(n_videos, dtype=t.int32, device='cuda')
+        self.details = None
+        if keep_details:     # (xmin,ymin,xmax,ymax,score) of every row: what track.py:190 unpacks for its overlay
+            self.details = t.zeros((n_videos, row_cap, 5), dtype=t.float64, device='cuda')
+            _lib.check(_lib.lib().vbt_tracker_row_details(self.handle, self.details.data_ptr()))
 
     def __del__(self):
         h, self.handle = getattr(self, 'handle', None), None

@@ -35,7 +35,7 @@ class VideoPipeline:
 
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
                  row_cap=1 << 17, id_lanes=32, tracker_kw=None, diff_threshold=0.6,
-                 min_distance=0.1, n_lanes=None):
+                 min_distance=0.1, n_lanes=None, keep_details=False):
         self.torch = t = _lib.require_cuda()
         if n_lanes is None:
             n_lanes = max(1, int(os.environ.get('VBT_LANES', '2')))
@@ -44,7 +44,9 @@ class VideoPipeline:
         self.threshold = float(detection_threshold)
         self.plate_diameter, self.diff_threshold, self.min_distance = plate_diameter, diff_threshold, min_distance
         self.F = detector.max_batch
-        self.tracker = BatchedTracker(1, row_cap=row_cap, **(tracker_kw or {}))
+        self.tracker = BatchedTracker(1, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
+        self.keep_details = keep_details
+        self._frame_log = []            # (frame numbers, detection counts) per batch, for the overlay export
         self.id_lanes = id_lanes
         self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
         D = detector.max_det
@@ -158,6 +160,8 @@ class VideoPipeline:
                 _lib.stream_ptr(ds)))
             self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
             self.n_frames[k].fill_(n)
+            if self.keep_details:
+                self._frame_log.append((self.frame_no[k, 0, :n].clone(), self.det_count[k, 0, :n].clone()))
             self._mark(marks)
             if not track:
                 if not hasattr(self, '_table'):
@@ -240,7 +244,17 @@ class VideoPipeline:
             if state[l, 2] > 0:
                 out_ph[l + 1] = _phases_from(phases[l], int(count[l]))
                 out_path[l + 1] = float(state[l, 3])
-        return dict(rows=rows, phases=out_ph, path=out_path)
+        out = dict(rows=rows, phases=out_ph, path=out_path)
+        if self.keep_details:
+            out['details'] = self.tracker.details[0, :len(rows)].cpu().numpy()
+            t = self.torch
+            if self._frame_log:
+                nos = t.cat([a for a, _ in self._frame_log]).cpu().numpy()
+                cnt = t.cat([b for _, b in self._frame_log]).cpu().numpy()
+                out['frames_with_results'] = [int(f) for f, c in zip(nos, cnt) if c > 0]
+            else:
+                out['frames_with_results'] = []
+        return out
 
 
 def rows_to_data(rows):
