@@ -233,8 +233,15 @@ def main():
     def one_step(src=None):
         b = state['cursor'] % n_batches
         if b == 0 and state['cursor'] > 0:
-            state['last'] = pipe.finish()          # end of the clip: phases + rows to the host
-            pipe.reset()
+            # end of the clip: end_processing() + rows / phases to the host.  next_video() queues
+            # that behind the clip's last tracker step and lets the next clip's batches enter the
+            # device at once; the hand-over collects the clip before it (long finished) -- nothing
+            # drains between videos.  VBT_BENCH_DRAIN=1: the synchronous finish() + reset() instead.
+            if os.environ.get('VBT_BENCH_DRAIN') == '1':
+                state['last'] = pipe.finish()
+                pipe.reset()
+            else:
+                state['pending'] = pipe.next_video()
             state['videos'] += 1
         s, e = batch_range(b)
         t0 = time.perf_counter()
@@ -280,6 +287,8 @@ def main():
     for _ in range(args.steps):
         one_step()
     host_ms = 1e3 * state['host_s'] / args.steps       # host time to ENQUEUE a step (process() only)
+    if state.get('pending') is not None:               # every finished clip reaches the host inside the timed region
+        state['last'] = state['pending'].result()
     current_wait_all()
     gather_tables()
     ev1.record()

@@ -304,3 +304,48 @@ def test_track_cli_writes_the_annotated_video(tmp_path):
     if 2 <= y0 < 238 and x1 - x0 > 8:
         edge = first[y0, x0 + 3:x1 - 3].astype(int)
         assert edge.mean() > 200, 'the top edge of the first box should be (nearly) white'
+
+
+def test_next_video_overlaps_and_equals_finish_reset():
+    """VideoPipeline.next_video(): three clips back to back without draining between them give,
+    per clip, exactly what finish() + reset() gives (fresh tracker and velocity state per video,
+    track.py:88-101,157), whatever order the handles are collected in."""
+    import torch
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    g = graph('lite0')
+    det = Detector(g, max_batch=8)
+    thr = 0.3
+    clips = [(30.0, synthetic_frames(n, 135, 240, seed=40 + i)) for i, n in enumerate((19, 8, 27, 5))]
+    clips[1] = (60.0, clips[1][1])
+
+    def feed(pipe, frames):
+        dev = torch.as_tensor(frames, device='cuda')
+        for s in range(0, len(frames), 8):
+            e = min(len(frames), s + 8)
+            pipe.process(dev[s:e], torch.arange(s + 1, e + 1, dtype=torch.int32, device='cuda'), swap_rb=True)
+
+    ref_pipe = VideoPipeline(det, clips[0][0], thr, row_cap=4096)
+    want = []
+    for fps, frames in clips:
+        ref_pipe.reset(fps)
+        feed(ref_pipe, frames)
+        want.append(ref_pipe.finish())
+    pipe = VideoPipeline(det, clips[0][0], thr, row_cap=4096)
+    handles = []
+    for i, (fps, frames) in enumerate(clips):
+        if i:
+            handles.append(pipe.next_video(fps))
+        feed(pipe, frames)
+    got = [None] * len(clips)
+    got[-1] = pipe.finish()
+    for i in reversed(range(len(handles))):          # out of order on purpose
+        got[i] = handles[i].result()
+    assert sum(len(w['rows']) for w in want) > 0
+    for i, (w, r) in enumerate(zip(want, got)):
+        assert np.array_equal(w['rows'], r['rows']), i
+        assert sorted(w['phases']) == sorted(r['phases']), i
+        for tid in w['phases']:
+            assert [(p.time_start, p.time_end, p.rom, p.type) for p in w['phases'][tid]] == \
+                   [(p.time_start, p.time_end, p.rom, p.type) for p in r['phases'][tid]]
+    assert np.array_equal(oracle_rows(g, clips[2][1], 30.0, thr), got[2]['rows'])

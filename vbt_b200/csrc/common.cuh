@@ -49,14 +49,29 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// high_priority: the launch (and the graph node captured from it) gets the device's greatest
+// priority, so its CTAs are dispatched ahead of pending CTAs of ordinary launches from OTHER
+// streams -- used for the small late-network kernels, which otherwise queue behind the other
+// detection lane's GPU-filling backbone kernels.
+inline int greatest_priority() {
+  static const int p = [] { int least = 0, greatest = 0; cudaDeviceGetStreamPriorityRange(&least, &greatest); return greatest; }();
+  return p;
+}
+
 template <typename Arg>
-cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg) {
+cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg,
+                       bool high_priority = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (high_priority) {
+    attr[1].id = cudaLaunchAttributePriority;
+    attr[1].val.priority = greatest_priority();
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, arg);
 }
 #endif

@@ -21,6 +21,41 @@ from .velocity import _Lanes, _phases_from
 COLUMNS = ['id', 'time', 'x', 'y', 'dx', 'dy', 'norm_plate_height', 'norm_plate_width']
 
 
+class _VideoState:
+    """Tracker + velocity state of ONE video.  The pipeline owns two and alternates, so the next
+    video's batches enter the device while the previous video's tail (last tracker steps,
+    end_processing, read-back) is still in flight -- `VideoPipeline.next_video`."""
+
+    def __init__(self, t, row_cap, id_lanes, keep_details, tracker_kw, fps=30.0):
+        # the tracker recurrence is one warp per video and nearly as long as a detection step: each
+        # video gets its own (high-priority) stream, so the tail of one video's recurrence runs
+        # beside the head of the next one's instead of in front of it
+        self.side = t.cuda.Stream(priority=-1)
+        self.d_fps = t.tensor([float(fps)], dtype=t.float64, device='cuda')
+        self.tracker = BatchedTracker(1, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
+        self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
+        self.lane_table = t.zeros(id_lanes, dtype=t.int32, device='cuda')
+        self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
+        self.frame_log = []             # (frame numbers, detection counts) per batch, for the overlay export
+        self.pending = None             # _PendingVideo not collected yet
+
+
+class _PendingVideo:
+    """A finished video whose results are still on the device; `result()` waits for its own tail
+    only (not for the videos that followed) and builds what `finish()` returns."""
+
+    def __init__(self, pipe, state, done):
+        self.pipe, self.state, self.done, self._res = pipe, state, done, None
+
+    def result(self):
+        if self._res is None:
+            t = self.pipe.torch
+            t.cuda.current_stream().wait_event(self.done)
+            self._res = self.pipe._collect(self.state)
+            self.state.pending = None
+        return self._res
+
+
 class VideoPipeline:
     """One video on one GPU.
 
@@ -28,10 +63,12 @@ class VideoPipeline:
     buffers) take the batches round robin, so two batches of the same video are in flight
     and one lane's small late-network kernels overlap the other's large early ones;
     tracking and velocity (K7, K8: a sequential recurrence over frames on one warp) follow
-    in batch order on the `side` stream, off the detector's critical path
-    (SURVEY.md 7.3-6).  Nothing returns to the host before `finish()`."""
+    in batch order on the video's `side` stream, off the detector's critical path
+    (SURVEY.md 7.3-6).  Nothing returns to the host before `finish()` / a `next_video()` handle."""
 
-    N_SLOTS = 4          # ring of tracker-input slots between the lanes and the side stream
+    # ring of tracker-input slots between the lanes and the side streams: deep enough that detection
+    # never waits for the tracker inside a 60 s clip (1.2 kB per frame and slot)
+    N_SLOTS = max(2, int(os.environ.get('VBT_SLOTS', '32')))
 
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
                  row_cap=1 << 17, id_lanes=32, tracker_kw=None, diff_threshold=0.6,
@@ -44,27 +81,23 @@ class VideoPipeline:
         self.threshold = float(detection_threshold)
         self.plate_diameter, self.diff_threshold, self.min_distance = plate_diameter, diff_threshold, min_distance
         self.F = detector.max_batch
-        self.tracker = BatchedTracker(1, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
         self.keep_details = keep_details
-        self._frame_log = []            # (frame numbers, detection counts) per batch, for the overlay export
         self.id_lanes = id_lanes
-        self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
+        self._state_args = (t, row_cap, id_lanes, keep_details, tracker_kw, self.fps)
+        self.states = [_VideoState(*self._state_args), _VideoState(*self._state_args)]
+        self.cur = 0
         D = detector.max_det
         S = self.N_SLOTS
         self.dets = t.zeros((S, 1, self.F, D, 6), dtype=t.float64, device='cuda')
         self.det_count = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
         self.frame_no = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
         self.n_frames = t.zeros((S, 1), dtype=t.int32, device='cuda')
-        self.d_fps = t.tensor([self.fps], dtype=t.float64, device='cuda')
-        self.lane_table = t.zeros(id_lanes, dtype=t.int32, device='cuda')
         self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda')
-        self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
         self.detectors = [detector] + [Detector(detector.source, max_batch=detector.max_batch,
                                                 iou_threshold=detector.iou_threshold,
                                                 max_det=detector.max_det) for _ in range(n_lanes - 1)]
         self.det_streams = [t.cuda.Stream() for _ in range(n_lanes)]
         self.active_lanes = n_lanes                  # bench.py profiles with a single lane
-        self.side = t.cuda.Stream()
         self.det_ready = [t.cuda.Event() for _ in range(S)]
         self.slot_free = [t.cuda.Event() for _ in range(S)]
         self.input_consumed = None     # event: the last batch's frames have been read (K1 / DMA done)
@@ -73,6 +106,15 @@ class VideoPipeline:
         self.last_slot = 0
         self.frames_done = 0
         self.stage_events = None      # bench.py: list of per-step event tuples when profiling
+
+    # the current video's state (what process() feeds)
+    tracker = property(lambda self: self.states[self.cur].tracker)
+    lanes = property(lambda self: self.states[self.cur].lanes)
+    lane_table = property(lambda self: self.states[self.cur].lane_table)
+    lane_begin = property(lambda self: self.states[self.cur].lane_begin)
+    _frame_log = property(lambda self: self.states[self.cur].frame_log)
+    side = property(lambda self: self.states[self.cur].side)
+    d_fps = property(lambda self: self.states[self.cur].d_fps)
 
     def use_row_sparse_ingest(self, H, W):
         """Host frames of this size are sent row-sparse (only the rows the resize reads)."""
@@ -93,7 +135,8 @@ class VideoPipeline:
         cur = self.torch.cuda.current_stream()
         for s in self.det_streams:
             cur.wait_stream(s)
-        cur.wait_stream(self.side)
+        for st in self.states:
+            cur.wait_stream(st.side)
 
     def reset(self, fps=None):
         t = self.torch
@@ -104,11 +147,13 @@ class VideoPipeline:
         self.tracker.reset()
         self.lanes.reset()
         self.lane_begin.zero_()
+        self._frame_log.clear()
         self.frames_done = 0
         cur = t.cuda.current_stream()
         for s in self.det_streams:
             s.wait_stream(cur)
-        self.side.wait_stream(cur)
+        for st in self.states:
+            st.side.wait_stream(cur)
 
     def process(self, frames, frame_numbers, swap_rb=True, track=True):
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
@@ -230,15 +275,51 @@ class VideoPipeline:
 
     def finish(self):
         """End of video: run end_processing() on every lane, bring results to the host.
-        Returns dict(rows=f64[n,8] append order, phases={id: [Phase]}, path={id: float})."""
+        Returns dict(rows=f64[n,8] append order, phases={id: [Phase]}, path={id: float}).
+        Synchronous: drains the whole pipeline.  `next_video()` is the overlapped form."""
         self._sync_streams()
-        self.tracker.check_status()
-        self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
-                          self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
-                          self.plate_diameter, self.diff_threshold, self.min_distance,
-                          smooth=True, finish=True)
-        phases, count, state = self.lanes.read()
-        rows = self.tracker.rows_host(0)
+        st = self.states[self.cur]
+        st.lanes.update(st.tracker.rows, st.tracker.row_count, st.tracker.row_cap,
+                        st.lane_table, self.lane_id, st.lane_begin, self.id_lanes,
+                        self.plate_diameter, self.diff_threshold, self.min_distance,
+                        smooth=True, finish=True)
+        return self._collect(st)
+
+    def next_video(self, fps=None):
+        """End of the current video WITHOUT draining the pipeline: its end_processing() is queued
+        behind its last tracker step on the side stream, the other state set is reset there too, and
+        the caller may feed the next video's frames at once.  Returns a handle whose `result()` gives
+        what `finish()` would have returned; a set's previous handle is collected before reuse."""
+        t = self.torch
+        st = self.states[self.cur]
+        with t.cuda.stream(st.side):
+            st.lanes.update(st.tracker.rows, st.tracker.row_count, st.tracker.row_cap,
+                            st.lane_table, self.lane_id, st.lane_begin, self.id_lanes,
+                            self.plate_diameter, self.diff_threshold, self.min_distance,
+                            smooth=True, finish=True)
+            done = t.cuda.Event()
+            done.record(st.side)
+        st.pending = pending = _PendingVideo(self, st, done)
+        self.cur ^= 1
+        nxt = self.states[self.cur]
+        if nxt.pending is not None:
+            nxt.pending.result()
+        nxt.side.wait_stream(t.cuda.current_stream())      # result() read the old tables on the current stream
+        if fps is not None:
+            self.fps = float(fps)
+        with t.cuda.stream(nxt.side):
+            nxt.tracker.reset()
+            nxt.lanes.reset()
+            nxt.lane_begin.zero_()
+            nxt.d_fps.fill_(self.fps)
+        nxt.frame_log.clear()
+        self.frames_done = 0
+        return pending
+
+    def _collect(self, st):
+        st.tracker.check_status()
+        phases, count, state = st.lanes.read()
+        rows = st.tracker.rows_host(0)
         out_ph, out_path = {}, {}
         for l in range(self.id_lanes):
             if state[l, 2] > 0:
@@ -246,11 +327,11 @@ class VideoPipeline:
                 out_path[l + 1] = float(state[l, 3])
         out = dict(rows=rows, phases=out_ph, path=out_path)
         if self.keep_details:
-            out['details'] = self.tracker.details[0, :len(rows)].cpu().numpy()
+            out['details'] = st.tracker.details[0, :len(rows)].cpu().numpy()
             t = self.torch
-            if self._frame_log:
-                nos = t.cat([a for a, _ in self._frame_log]).cpu().numpy()
-                cnt = t.cat([b for _, b in self._frame_log]).cpu().numpy()
+            if st.frame_log:
+                nos = t.cat([a for a, _ in st.frame_log]).cpu().numpy()
+                cnt = t.cat([b for _, b in st.frame_log]).cpu().numpy()
                 out['frames_with_results'] = [int(f) for f, c in zip(nos, cnt) if c > 0]
             else:
                 out['frames_with_results'] = []

@@ -98,11 +98,15 @@ def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank
     pipe = None
     local, phases = {}, {}
     B = detector.max_batch
+    handles = []                     # (video index, pending result): videos overlap, nothing drains between them
+    prev = None
     for vi in plan[rank]:
         v = videos[vi]
         if pipe is None:
             pipe = VideoPipeline(detector, v['fps'], detection_threshold, **pipe_kw)
-        pipe.reset(v['fps'])
+        else:
+            handles.append((prev, pipe.next_video(v['fps'])))     # fresh tracker per source (track.py:157)
+        prev = vi
         frames = v['frames']
         n = int(frames.shape[0])
         # 1-based frame_count of the kept frames (track.py:161,166)
@@ -112,9 +116,12 @@ def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank
             idx = keep[s:s + B].long() - 1
             chunk = frames[idx[0]:idx[-1] + 1] if frame_stride == 1 else frames[idx.to(frames.device)]
             pipe.process(chunk.contiguous(), numbers[s:s + B], swap_rb=True)
-        res = pipe.finish()
-        local[vi] = res['rows']
-        phases[vi] = res['phases']
+    if pipe is not None:
+        last = pipe.finish()
+        for vi, h in handles:
+            res = h.result()
+            local[vi], phases[vi] = res['rows'], res['phases']
+        local[prev], phases[prev] = last['rows'], last['phases']
     tables = gather_row_tables(local, len(videos), group=group)
     return tables, phases
 
