@@ -70,6 +70,8 @@ class ClockSampler:
         self.index, self.proc, self.lines = index, None, []
 
     def start(self):
+        if self.index is None:
+            return
         try:
             self.proc = subprocess.Popen(
                 ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
@@ -273,7 +275,9 @@ def main():
     # ---- device-resident throughput (`value`) -------------------------------------------
     for _ in range(max(args.warmup, 3)):          # >= 3: direct run, graph capture, first replay
         one_step()
-    sampler = ClockSampler(local_rank)
+    # one sampler per job (rank 0's GPU): eight nvidia-smi loops on one host steal the cores the
+    # ranks enqueue from and serialise on the driver's NVML lock
+    sampler = ClockSampler(local_rank if rank == 0 else None)
     barrier()
     sampler.start()
     launches0 = _lib.lib().vbt_launch_count()
