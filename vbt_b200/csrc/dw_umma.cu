@@ -73,8 +73,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+constexpr int kDwThreads = 256;    // 8 warps: warp w owns TMEM lanes 32 * (w % 4) .., channel group w / 4 of the pair
+
 template <bool FAST>
-__global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
+__global__ void __launch_bounds__(kDwThreads) dw_umma_kernel(DwUArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long mbar[kMaxTiles];
   __shared__ uint32_t tmem_base_s;
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
   }
   {
     const int4* src = reinterpret_cast<const int4*>(a.wdiag + (size_t)gp * taps * 1024);
-    for (int i = tid; i < taps * 64; i += 128) {
+    for (int i = tid; i < taps * 64; i += kDwThreads) {
       const uint32_t dst = smem_u32(wsm) + (uint32_t)i * 16;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + i));
     }
@@ -124,7 +126,7 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
     for (int pl = 0; pl < n_planes; ++pl) {
       const int pr = pl >> ss, pc = pl & ss;           // S = 2: pl = pr * 2 + pc; S = 1: 0, 0
       unsigned char* p0 = planes + (size_t)(pl * 2) * plane_bytes;
-      for (int i = tid; i < n_slots; i += 128) {
+      for (int i = tid; i < n_slots; i += kDwThreads) {
         const int ly = (int)__umulhi((uint32_t)i, a.inv_pw);
         const int lx = i - ly * a.PW;
         const int iy = (((oy0 + ly) << ss) + pr) - a.pad_top;
@@ -172,39 +174,36 @@ __global__ void __launch_bounds__(128) dw_umma_kernel(DwUArgs a) {
     }
   }
 
-  // ---- epilogue: thread t owns position mt*128 + t ---------------------------------------------
-  const bool has_g1 = gp * 2 + 1 < a.groups;
+  // ---- epilogue: thread t owns position mt*128 + (t % 128) and channel group t / 128 of the pair --
+  const int row = tid & 127, half = tid >> 7;
+  const bool has_group = gp * 2 + half < a.groups;
   for (int mt = 0; mt < a.n_mt; ++mt) {
     if (warp == 0) mbar_wait(smem_u32(&mbar[mt]), 0);   // one warp polls, the others sleep on the barrier
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n");
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)mt * 32;
-    uint32_t v[32];
+    const uint32_t taddr = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)mt * 32 + (uint32_t)half * 16;
+    uint32_t v[16];
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
-        "%14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+        "%13, %14, %15}, [%16];\n"
         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
-          "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-          "=r"(v[30]), "=r"(v[31])
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-    const int q = mt * 128 + tid;
+    const int q = mt * 128 + row;
     const int ly = (int)__umulhi((uint32_t)q, a.inv_pw);
     const int lx = q - ly * a.PW;
-    if (ly < th && lx < a.Wo) {
-      uint32_t packed[8];
+    if (has_group && ly < th && lx < a.Wo) {
+      uint32_t packed[4];
 #pragma unroll
-      for (int w4 = 0; w4 < 8; ++w4) {
-        const int4 bq = *reinterpret_cast<const int4*>(sBias + w4 * 4);
-        const float4 mq = *reinterpret_cast<const float4*>(sMult + w4 * 4);
+      for (int w4 = 0; w4 < 4; ++w4) {
+        const int4 bq = *reinterpret_cast<const int4*>(sBias + half * 16 + w4 * 4);
+        const float4 mq = *reinterpret_cast<const float4*>(sMult + half * 16 + w4 * 4);
         packed[w4] = a.rq.pack4t<FAST>((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
-                                (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
+                                       (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
       }
-      int8_t* o = a.out + (((size_t)b * a.Ho + oy0 + ly) * a.Wo + lx) * a.c_p + gp * 32;
+      int8_t* o = a.out + (((size_t)b * a.Ho + oy0 + ly) * a.Wo + lx) * a.c_p + gp * 32 + half * 16;
       *reinterpret_cast<uint4*>(o) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-      if (has_g1) *reinterpret_cast<uint4*>(o + 16) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -270,8 +269,8 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
     attr_set = true;
   }
   dim3 grid((unsigned)a.n_bands, (unsigned)a.pairs, (unsigned)B);
-  if (a.rq.fast) VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<true>, grid, dim3(128), smem, st, a));
-  else VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<false>, grid, dim3(128), smem, st, a));
+  if (a.rq.fast) VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<true>, grid, dim3(kDwThreads), smem, st, a));
+  else VBT_CHECK_CUDA(launch_pdl(dw_umma_kernel<false>, grid, dim3(kDwThreads), smem, st, a));
   *taken = true;
   return VBT_OK;
 }
