@@ -20,10 +20,11 @@ The file is walked operator by operator and mapped onto the ops libvbt_b200.so e
 
 PARITY UNPINNED [3P-MEM]: no `.tflite` written by TensorFlow exists in this container (the
 reference's blobs are listed in .MISSING_LARGE_BLOBS), so the reader is only proven against files
-written by tflite_writer.py.  Where TFLite's kernels use a different arithmetic than ours (the
-int8 ADD is a two-stage fixed-point rescale there, a single integer multiply-shift here) results
-may differ by one quantisation step; the north star's tolerance for real weights (IoU >= 0.99,
-|dscore| <= 1e-2) is the bar for such files, not bit equality.
+written by tflite_writer.py.  The integer semantics follow the XNNPACK delegate tflite_runtime
+2.14 applies by default (fp32 requantisation of the convolutions, single multiply-shift qs8 ADD);
+TFLite's built-in reference / optimised kernels use gemmlowp fixed-point multipliers and a
+two-stage ADD instead and may differ by one quantisation step.  The north star's tolerance for
+real weights (IoU >= 0.99, |dscore| <= 1e-2) is the bar for files from TensorFlow, not bit equality.
 """
 from __future__ import annotations
 
