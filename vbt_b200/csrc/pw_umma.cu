@@ -296,7 +296,13 @@ int launch_pw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, con
   // measured on B200 (VBT_PW_NC sweep, profiles/): 128-256 beats 32-96 by 5-20 %.
   static const int nc_max = [] { const char* e = getenv("VBT_PW_NC"); int v = e ? atoi(e) : 256;
                                  return v < 16 ? 16 : (v > 256 ? 256 : v / 16 * 16); }();
-  const int n_chunks = (op.cout_p + nc_max - 1) / nc_max;
+  int n_chunks = (op.cout_p + nc_max - 1) / nc_max;
+  // small grids (the 10x10 stage: 50 row tiles): narrower N chunks until every SM has a CTA
+  static const bool fill = [] { const char* e = getenv("VBT_PW_FILL"); return !(e && e[0] == '0'); }();
+  {
+    const long long tiles = (a.M + TILE_M - 1) / TILE_M;
+    while (fill && tiles * n_chunks < 148 && (op.cout_p + n_chunks) / (n_chunks + 1) >= 32) ++n_chunks;
+  }
   a.nc = ((op.cout_p + n_chunks - 1) / n_chunks + 15) / 16 * 16;
   const bool has_res = res != nullptr;
   a.zp_conv = op.zp_out; a.lo = op.act_lo; a.hi = op.act_hi;
