@@ -146,7 +146,7 @@ def test_requant_ties_and_both_paths(mult, fast, zp_out):
 # ---- persistent warp-specialised pointwise kernel (csrc/pw_persist.cu) -------------------------
 
 def test_pointwise_persistent_kernel():
-    """pw_persist.cu (opt-in: VBT_PW_PERSIST=1) takes large-M, K <= 256 layers; MIN_TILES=1 forces it for
+    """pw_persist.cu takes the large-M, K <= 256 layers; VBT_PW_PERSIST_MIN_TILES=1 forces it for
     every eligible shape here: M tails, one tile, many tiles per CTA (ring and accumulator phases
     wrap several times), odd K chunk counts, two N chunks, residual epilogue.  The env var is read
     once per process, hence the subprocess."""

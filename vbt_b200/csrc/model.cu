@@ -97,6 +97,15 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
     delete m;
     return VBT_ECUDA;
   }
+  if (hdr.n_ops > 0) {
+    const size_t cbytes = sizeof(int32_t) * 16 * (size_t)hdr.n_ops * vbt_model::kCounterSlots;
+    if (cudaMalloc(&m->dev_counters, cbytes) != cudaSuccess || cudaMemset(m->dev_counters, 0, cbytes) != cudaSuccess) {
+      set_error("vbt_model_create: allocating the scheduler counters failed");
+      cudaFree(m->dev_data);
+      delete m;
+      return VBT_ECUDA;
+    }
+  }
   m->dev_anchors = reinterpret_cast<const float*>(m->dev_data + hdr.anchors_off);
   m->dev_exp_lut = reinterpret_cast<const float*>(m->dev_data + hdr.exp_lut_off);
   m->kernels_per_detect = hdr.n_ops;
@@ -201,6 +210,7 @@ void vbt_model_destroy(vbt_model* m) {
   for (int k = 0; k < vbt_model::kMaxBranches; ++k)
     if (m->fork_event[k]) cudaEventDestroy(m->fork_event[k]);
   if (m->dev_data) cudaFree(m->dev_data);
+  if (m->dev_counters) cudaFree(m->dev_counters);
   delete m;
 }
 

@@ -106,6 +106,13 @@ struct vbt_model {
   // launch plan: fuse[i] = number of consecutive ops the launch starting at op i covers
   // ([ADD ->] DW3x3 -> PW on small maps run as one node_umma kernel), 0 for ops inside a group
   std::vector<int> fuse;
+  // work counters of the persistent kernels' dynamic tile schedulers: 16 ints per (workspace, op),
+  // all zero between launches (the last CTA of a launch puts them back).  One block of n_ops * 16
+  // per workspace the model has been run on, so concurrent lanes never share a counter.
+  static constexpr int kCounterSlots = 8;
+  int32_t* dev_counters = nullptr;            // [kCounterSlots][n_ops][16]
+  std::vector<const void*> counter_owner;     // workspace pointer of each slot in use
+  mutable int32_t* cur_counters = nullptr;    // the current op's 16 counters (set by run_ops)
   // CUDA graphs of the layer program, one per (buffers, batch) a caller has used twice
   struct GraphKey {
     const void *in, *ws, *cls, *box; int B;

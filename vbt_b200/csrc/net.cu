@@ -500,8 +500,17 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
   bool started[vbt_model::kMaxBranches] = {};
   if (prof) VBT_CHECK_CUDA(cudaEventRecord(prof[0], main_st));
   const int n_ops = (int)m->ops.size();
+  // scheduler counters of this workspace (a lane): -1 = all slots taken, persistent kernels stay off
+  int cslot = -1;
+  for (size_t i = 0; i < m->counter_owner.size(); ++i)
+    if (m->counter_owner[i] == dev_workspace) cslot = (int)i;
+  if (cslot < 0 && (int)m->counter_owner.size() < vbt_model::kCounterSlots) {
+    m->counter_owner.push_back(dev_workspace);
+    cslot = (int)m->counter_owner.size() - 1;
+  }
   for (int oi = 0; oi < n_ops; ++oi) {
     const OpRecord& op = m->ops[oi];
+    m->cur_counters = (cslot >= 0 && m->dev_counters) ? m->dev_counters + ((size_t)cslot * n_ops + oi) * 16 : nullptr;
     cudaStream_t st = main_st;
     if (fork && op.branch > 0) {
       const int k = op.branch - 1;

@@ -23,13 +23,14 @@
 //     pw_umma.cu on the wide expand layers), hence E.
 // Loads, MMAs and epilogues of consecutive tiles overlap; nothing is re-loaded per tile.
 //
-// STATUS: opt-in (VBT_PW_PERSIST=1), parity-tested, NOT the default.  Measured on B200 (Lite0,
-// frame batch 64, profiles/r1_pw_persist_*.txt): the narrow project layers gain (b2.0.project
-// 44.6 -> 33.8 us, b1.0.project 80 -> 72 us) but the wide expand layers lose (b2.0.expand 105 ->
-// 141 us): ncu shows both kernels at ~0.76 IPC per scheduler with math_pipe_throttle on the
-// requantisation's integer / min-max / permute instructions (ALU pipe, half the FMA pipe's
-// rate) -- the epilogue arithmetic, not the tile life cycle, is the floor, and the short-lived
-// CTAs of pw_umma.cu spread it over more warps.
+// STATUS: default for eligible layers (VBT_PW_PERSIST=0 switches it off).  History, measured on
+// B200 (Lite0, frame batch 64; profiles/r1_pw_persist_*.txt): with tiles dealt by a
+// fixed stride the kernel LOST to pw_umma.cu (b2.0.expand 105 -> 141 us): cycle counters in the
+// three roles showed a resident CTA needs 62 us for its 43 tiles, but not all 296 CTAs become
+// resident at once (other kernels' CTAs still hold shared memory / TMEM on some SMs), and with a
+// fixed stride the stragglers' tiles waited for a second wave.  With the atomic tile counter a
+// late CTA just takes fewer tiles: b1.0.project 80 -> 57 us, b2.1.expand 72 -> 55, b2.0.project
+// 45 -> 30, b2.0.expand 105 -> 105; the pipeline gains 2.3 % (36.8 k -> 37.7 k frames/s).
 #include "model.cuh"
 #include "requant.cuh"
 
@@ -40,6 +41,7 @@ using vbt::OpRecord;
 constexpr int TILE_M = 128;
 constexpr int MAX_NT = 64 + 128 * 4; // producer warp, MMA warp, 4 * E epilogue warps
 constexpr int MAX_STAGES = 4;
+constexpr int MAX_ACC = 8;           // TMEM accumulators in flight per CTA
 
 struct PwPersistArgs {
   const int8_t* in; const int8_t* res; int8_t* out;
@@ -50,6 +52,7 @@ struct PwPersistArgs {
   int kpad;                     // 16-byte K chunks, rounded up to even
   int stages;
   int epi;                      // E: epilogue warps per TMEM lane quarter
+  int n_acc;                    // TMEM accumulators (2 .. MAX_ACC): tiles between MMA issue and read-back
   int acc_cols;                 // TMEM columns per accumulator (>= nc)
   int tmem_cols;                // allocation: power of two >= 2 * acc_cols
   int zp_conv, lo, hi;
@@ -57,6 +60,7 @@ struct PwPersistArgs {
   int out_stride;               // staging row stride in bytes (odd multiple of 16)
   uint32_t inv_kpad, inv_cpr;   // ceil(65536 / kpad), ceil(65536 / (nc / 16))
   vbt::Requant rq;
+  int32_t* counters;            // [16] zero between launches: [0] CTAs done, [1 + y] next tile of N chunk y
 };
 
 __device__ __forceinline__ int div_small(int q, uint32_t inv) { return (int)(((uint32_t)q * inv) >> 16); }
@@ -106,8 +110,9 @@ template <bool HAS_RES>
 __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_full[MAX_STAGES], bar_empty[MAX_STAGES];
-  __shared__ __align__(8) unsigned long long bar_acc_full[2], bar_acc_empty[2];
+  __shared__ __align__(8) unsigned long long bar_acc_full[MAX_ACC], bar_acc_empty[MAX_ACC];
   __shared__ uint32_t tmem_base_s;
+  __shared__ int sTile[16];          // tile of the i-th work item of this CTA (ring), -1 = no more work
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int NT = (int)blockDim.x;
   const int n0 = blockIdx.y * a.nc;
@@ -130,10 +135,10 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
   }
   if (tid == 32) {
     for (int s = 0; s < a.stages; ++s) {
-      mbar_init(smem_u32(&bar_full[s]), 32);
+      mbar_init(smem_u32(&bar_full[s]), 33);           // 32 copy completions + the producer's own arrival
       mbar_init(smem_u32(&bar_empty[s]), 1);
     }
-    for (int b = 0; b < 2; ++b) {
+    for (int b = 0; b < a.n_acc; ++b) {
       mbar_init(smem_u32(&bar_acc_full[b]), 1);
       mbar_init(smem_u32(&bar_acc_empty[b]), 4 * a.epi);
     }
@@ -161,27 +166,38 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
   vbt::pdl_wait();                 // activations / residual / output buffer belong to predecessors until here
   vbt::pdl_launch_dependents();
 
-  const int first = blockIdx.x, step = gridDim.x;
   if (warp == 0) {
     // ---- producer -----------------------------------------------------------------------------
     const int items = TILE_M * kpad;                  // 16-byte granules per A tile (shared: linear)
     // Each lane's cp.async.mbarrier.arrive.noinc makes full[s] count that lane's copies as they
     // land: the producer never blocks on its own loads, so a tile is announced the moment it is
     // in shared memory and the only thing the producer ever waits for is a free stage.
+    // Tiles are handed out by an atomic counter, not by a fixed stride: a CTA that becomes resident
+    // late (its SM still held CTAs of another kernel, or another stream's) simply takes fewer
+    // tiles instead of making the whole launch wait for a second wave.
     int issued = 0;
-    for (int tile = first; tile < a.n_tiles; tile += step, ++issued) {
+    for (;; ++issued) {
       const int s = issued % a.stages;
       mbar_wait(smem_u32(&bar_empty[s]), (((uint32_t)(issued / a.stages)) & 1) ^ 1);
-      const long long m0 = (long long)tile * TILE_M;
-      const uint32_t dst0 = smem_u32(sA) + (uint32_t)s * a_bytes;
-      for (int it = lane; it < items; it += 32) {
-        const int rr = it & 7, q = it >> 3;
-        const int g = div_small(q, a.inv_kpad), kc = q - g * kpad;
-        const long long m = m0 + g * 8 + rr;
-        const bool ok = (m < a.M) && (kc < kch);
-        cp_async16(dst0 + (uint32_t)it * 16, a.in + (ok ? m : 0) * a.cin_p + (size_t)(ok ? kc : 0) * 16, ok);
+      int tile = 0;
+      if (lane == 0) tile = atomicAdd(a.counters + 1 + blockIdx.y, 1);
+      tile = __shfl_sync(0xffffffffu, tile, 0);
+      const bool more = tile < a.n_tiles;
+      if (lane == 0) sTile[issued & 15] = more ? tile : -1;
+      if (more) {
+        const long long m0 = (long long)tile * TILE_M;
+        const uint32_t dst0 = smem_u32(sA) + (uint32_t)s * a_bytes;
+        for (int it = lane; it < items; it += 32) {
+          const int rr = it & 7, q = it >> 3;
+          const int g = div_small(q, a.inv_kpad), kc = q - g * kpad;
+          const long long m = m0 + g * 8 + rr;
+          const bool ok = (m < a.M) && (kc < kch);
+          cp_async16(dst0 + (uint32_t)it * 16, a.in + (ok ? m : 0) * a.cin_p + (size_t)(ok ? kc : 0) * 16, ok);
+        }
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(&bar_full[s])) : "memory");
+      if (lane == 0) mbar_arrive(smem_u32(&bar_full[s]));     // releases sTile[] to the MMA thread
+      if (!more) break;
     }
     asm volatile("cp.async.wait_all;\n" ::: "memory");
   } else if (warp == 1) {
@@ -190,11 +206,14 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(nc >> 3) << 17) |
                              ((uint32_t)(TILE_M >> 4) << 24);
       const uint32_t sbo = (uint32_t)kpad * 128;
-      int it_tile = 0;
-      for (int tile = first; tile < a.n_tiles; tile += step, ++it_tile) {
-        const int s = it_tile % a.stages, b = it_tile & 1;
-        mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)it_tile >> 1) & 1) ^ 1);
+      for (int it_tile = 0;; ++it_tile) {
+        const int s = it_tile % a.stages, b = it_tile % a.n_acc;
+        mbar_wait(smem_u32(&bar_acc_empty[b]), (((uint32_t)(it_tile / a.n_acc)) & 1) ^ 1);
         mbar_wait(smem_u32(&bar_full[s]), ((uint32_t)(it_tile / a.stages)) & 1);
+        if (sTile[it_tile & 15] < 0) {                // no more work: pass the word on to the epilogue
+          mbar_arrive(smem_u32(&bar_acc_full[b]));
+          break;
+        }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // cp.async (generic proxy) -> MMA reads
         asm volatile("tcgen05.fence::after_thread_sync;\n");
         const uint32_t abase = smem_u32(sA) + (uint32_t)s * a_bytes;
@@ -218,9 +237,11 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
     const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
     int last_c0 = -1;                                 // this warp's last chunk (none: nc too narrow)
     for (int c0 = slice * 16; c0 < nc; c0 += 16 * E) last_c0 = c0;
-    int it_tile = 0;
-    for (int tile = first; tile < a.n_tiles; tile += step, ++it_tile) {
-      const int b = it_tile & 1;
+    for (int it_tile = 0;; ++it_tile) {
+      const int b = it_tile % a.n_acc;
+      mbar_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)(it_tile / a.n_acc)) & 1);
+      const int tile = sTile[it_tile & 15];
+      if (tile < 0) break;
       const long long mw = (long long)tile * TILE_M + quarter * 32;   // first row of this quarter
       if (HAS_RES) {                                  // residual rows, coalesced, into the staging buffer
         for (int i = qt; i < 32 * cpr; i += 32 * E) {
@@ -231,7 +252,6 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
         }
         asm volatile("bar.sync %0, %1;\n" ::"r"(bar_id), "r"(bar_n) : "memory");
       }
-      mbar_wait(smem_u32(&bar_acc_full[b]), ((uint32_t)it_tile >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n");
       const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16) + (uint32_t)b * a.acc_cols;
       if (last_c0 < 0) {                              // nothing to read: still hand the accumulator back
@@ -291,6 +311,15 @@ __global__ void __launch_bounds__(MAX_NT) pw_persist_kernel(PwPersistArgs a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
+  if (tid == 0) {                                     // the last CTA of the launch zeroes the counters again
+    __threadfence();
+    const int done = atomicAdd(a.counters, 1);
+    if (done == (int)(gridDim.x * gridDim.y) - 1) {
+      for (int i = 1; i < 16; ++i) a.counters[i] = 0;
+      __threadfence();
+      a.counters[0] = 0;
+    }
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem),
                  "r"((uint32_t)a.tmem_cols));
@@ -305,15 +334,16 @@ namespace vbt {
 int launch_pw_persist(const vbt_model* m, const OpRecord& op, const int8_t* in, const int8_t* res, int8_t* out,
                       int B, cudaStream_t st, bool* taken) {
   *taken = false;
-  static const int enabled = [] { const char* e = getenv("VBT_PW_PERSIST"); return e ? atoi(e) : 0; }();
+  static const int enabled = [] { const char* e = getenv("VBT_PW_PERSIST"); return e ? atoi(e) : 1; }();
   static const int min_tiles = [] { const char* e = getenv("VBT_PW_PERSIST_MIN_TILES"); return e ? atoi(e) : 592; }();
-  if (!enabled || op.out_kind != 0 || op.lut_off >= 0) return VBT_OK;
+  if (!enabled || op.out_kind != 0 || op.lut_off >= 0 || !m->cur_counters) return VBT_OK;
   if (op.cin_p % 16 || op.cout_p % 16 || op.cout_p < 16 || op.cin_p > 256) return VBT_OK;
   PwPersistArgs a;
   a.M = (long long)B * op.h_in * op.w_in;
   a.n_tiles = (int)((a.M + TILE_M - 1) / TILE_M);
   if (a.n_tiles < min_tiles) return VBT_OK;
   a.in = in; a.res = res; a.out = out;
+  a.counters = m->cur_counters;
   a.w = reinterpret_cast<const int8_t*>(m->dev_data + op.w_off);
   a.bias = reinterpret_cast<const int32_t*>(m->dev_data + op.bias_off);
   a.mult = reinterpret_cast<const float*>(m->dev_data + op.scale_off);
@@ -334,8 +364,17 @@ int launch_pw_persist(const vbt_model* m, const OpRecord& op, const int8_t* in, 
   a.epi = a.nc >= 64 ? 4 : (a.nc >= 32 ? 2 : 1);
   if (epi_env == 1 || epi_env == 2 || epi_env == 4) a.epi = epi_env;
   const int NT = 64 + 128 * a.epi;
+  static const int acc_env = [] { const char* e = getenv("VBT_PW_ACC"); return e ? atoi(e) : 0; }();
+  // accumulators: 2 per CTA with two CTAs per SM, or (VBT_PW_ACC=n) n per CTA from all 512 columns
+  a.n_acc = 2;
   int cols = 32;
-  while (cols < 2 * a.acc_cols) cols <<= 1;
+  if (acc_env >= 2) {
+    a.n_acc = std::min(std::min(acc_env, MAX_ACC), 512 / a.acc_cols);
+    if (a.n_acc < 2) return VBT_OK;
+    cols = 512;
+  } else {
+    while (cols < 2 * a.acc_cols) cols <<= 1;
+  }
   a.tmem_cols = cols;
   a.inv_kpad = (65536u + a.kpad - 1) / a.kpad;
   a.inv_cpr = (65536u + a.nc / 16 - 1) / (a.nc / 16);
