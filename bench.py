@@ -486,6 +486,17 @@ def main():
         cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': f'first {n} frames of the same clip, one frame per invoke like track.py; '
                          f'int8-exact oracle chain (numpy + torch-CPU fp64 conv), not TFLite/XNNPACK'}
+        # the reference's own default is --threads 4 (track.py:72): the same port on four threads
+        all_threads = torch.get_num_threads()
+        if all_threads > 4 and n >= 4:
+            torch.set_num_threads(4)
+            cp.reset()
+            t0 = time.perf_counter()
+            for i in range(min(n, 4)):
+                cp.step(sample[i], i + 1)
+            cp.finish()
+            cpu['value_4_threads'] = min(n, 4) / (time.perf_counter() - t0)
+            torch.set_num_threads(all_threads)
 
     if rank == 0:
         out = {
