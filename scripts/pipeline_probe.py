@@ -5,7 +5,6 @@ velocity stream attached, (c) the tracker stream alone on the recorded detection
 usage (on a B200): python scripts/pipeline_probe.py"""
 import os
 import sys
-import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -2,7 +2,6 @@
 the writer and the reader against each other.  No file written by TensorFlow exists in this
 container (the reference's six models are listed in .MISSING_LARGE_BLOBS), so what is pinned here
 is self-consistency: a model exported and re-imported computes bit-identical outputs."""
-import struct
 
 import numpy as np
 import pytest
