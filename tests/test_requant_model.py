@@ -1,0 +1,48 @@
+"""The packed requantisation of csrc/requant.cuh (Requant::pack4t<true>), restated in numpy float32
+and checked against the plain definition  y = clamp(rne(float32(acc) * M) + zp, lo, hi)  -- the
+arithmetic argument of the kernel comment, executed: magic-number rounding with the 2^15 bias,
+unsigned 16-bit clamp, zero point added as an integer afterwards, low byte taken."""
+import numpy as np
+import pytest
+
+MAGIC_BITS = 0x4B400000          # bits of 1.5 * 2^23
+
+
+def plain(acc, mult, zp, lo, hi):
+    p = acc.astype(np.float32) * mult.astype(np.float32)
+    return np.clip(np.rint(p).astype(np.int64) + zp, lo, hi)
+
+
+def packed(acc, mult, zp, lo, hi):
+    p = acc.astype(np.float32) * mult.astype(np.float32)                 # FMUL (scalar: no FFMA2 contraction)
+    q = (p + np.float32(12582912.0 + 32768.0)).astype(np.float32)        # FADD2: rounds p like rint()
+    half = q.view(np.uint32) & 0xFFFF                                    # PRMT: low 16 bits = rint(p) + 2^15
+    lo16, hi16 = lo - zp + 32768, hi - zp + 32768
+    half = np.minimum(np.maximum(half, lo16), hi16)                      # VIMNMX.U16x2
+    half = (half + (zp & 0xFFFF)) & 0xFFFF                               # 32-bit add of zp * 0x10001: no carry between halves
+    return ((half & 0xFF).astype(np.uint8)).view(np.int8).astype(np.int64)   # PRMT 0x6420: the low byte is the int8
+
+
+@pytest.mark.parametrize('zp,lo,hi', [(11, -128, 127), (-128, -128, 95), (-20, -20, 107), (127, 0, 127), (-3, -128, 127)])
+def test_packed_equals_plain(zp, lo, hi):
+    rng = np.random.default_rng(zp + 200)
+    mult = rng.uniform(1e-5, 2e-2, 4096).astype(np.float32)
+    acc = np.rint(rng.uniform(-1, 1, 4096) * 31000.0 / mult).astype(np.int64).clip(-2**31, 2**31 - 1).astype(np.int32)
+    assert np.abs(acc.astype(np.float32) * mult).max() < 32000             # the bound pack_blob proves per op
+    assert np.array_equal(packed(acc, mult, zp, lo, hi), plain(acc, mult, zp, lo, hi))
+
+
+@pytest.mark.parametrize('zp', [11, -20, -127, 0, 126])
+def test_ties_go_to_even_before_the_zero_point(zp):
+    """acc * M exactly on .5: rint() goes to the even integer of p, whatever the parity of zp --
+    which is why the zero point is NOT folded into the magic constant."""
+    acc = np.arange(-4001, 4001, 2, dtype=np.int32)                          # odd accumulators
+    for m in (0.5, 0.25, 0.125):
+        mult = np.full(acc.shape, m, np.float32)
+        a = acc * int(1 / m) // 2 * 2 + 1 if m != 0.5 else acc
+        a = a.astype(np.int32)
+        assert np.array_equal(packed(a, mult, zp, -128, 127), plain(a, mult, zp, -128, 127))
+    # folding zp into the float add would break odd zero points on ties
+    p = np.float32(0.5)
+    folded = int((np.float32(p + np.float32(12582912.0 + 1))).view(np.uint32)) - MAGIC_BITS   # zp = 1
+    assert folded == 2 and int(np.rint(p)) + 1 == 1
