@@ -347,20 +347,26 @@ def main():
     # time is recorded on its first op; its algorithmic bytes are the run's inputs + its output +
     # the weights -- the intermediates never leave the SM
     plan = det.plan()
+    kinds = det.plan_kinds()
     op_class = []
     for i, op in enumerate(g.ops):
         name, by, fl = op_algorithmic(g, op, effdet)
         if plan[i] > 1:
             run = g.ops[i:i + plan[i]]
-            name = 'node_fused'
+            name = 'mbconv_fused' if kinds[i] == 1 else 'node_fused'
             produced = {o.out for o in run}
-            first_in = sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c
-                           for o in run for t in o.inputs if t not in produced)
+            ext = []
+            for o in run:
+                for t in o.inputs + ([o.residual] if o.residual >= 0 else []):
+                    if t not in produced and (kinds[i] != 1 or t not in ext):   # a block reads its input once
+                        ext.append(t)
+            first_in = sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c for t in ext)
             last = run[-1]
             t_in = g.tensors[last.inputs[0]]
             out_el = (g.tensors[last.out].h * g.tensors[last.out].w * g.tensors[last.out].c) if last.out >= 0 \
                 else t_in.h * t_in.w * g.out_channels(last)
-            wts = sum(op_algorithmic(g, o, effdet)[1] - sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c for t in o.inputs)
+            wts = sum(op_algorithmic(g, o, effdet)[1] - sum(g.tensors[t].h * g.tensors[t].w * g.tensors[t].c
+                                                            for t in o.inputs + ([o.residual] if o.residual >= 0 else []))
                       - ((g.tensors[o.out].h * g.tensors[o.out].w * g.tensors[o.out].c) if o.out >= 0
                          else g.tensors[o.inputs[0]].h * g.tensors[o.inputs[0]].w * g.out_channels(o))
                       for o in run if o.type != effdet.OP_ADD)

@@ -79,6 +79,9 @@ int vbt_model_info(const vbt_model* m, long long info[8]);
 /* launch plan: group_len i32 [ops] on the host; group_len[i] = number of consecutive ops the
  * kernel launched at op i covers (fused [ADD ->] DW3x3 -> PW groups), 0 for ops inside a group */
 int vbt_model_plan(const vbt_model* m, int32_t* host_group_len);
+/* kind i32 [ops] of the launch that starts at op i: 0 = a single op or a fused BiFPN node / head
+ * stage, 1 = a whole MBConv block ([1x1 expand ->] depthwise -> 1x1 project [+ residual]) */
+int vbt_model_plan_kinds(const vbt_model* m, int32_t* host_kind);
 /* in: u8 [B,S,S,3] RGB; out_cls: i8 [B,Np] post-LOGISTIC scores (scale 1/256, zp -128);
  * out_box: i8 [B,Np,4] (ty,tx,th,tw) with the model's box quantisation; Np = info[6] =
  * N rounded up to 16 (row stride; the pad entries are never read).

@@ -143,6 +143,39 @@ def node_graph(h, w, c, n_in=3, seed=0, odd=False, tree=False):
     return g
 
 
+def mbconv_graph(h, w, cin, cexp, cout, k, stride, residual=False, seed=0, expand=True):
+    """input -> PW(cin->cexp, ReLU6) -> DW kxk stride s (ReLU6) -> PW(cexp->cout) [+ input]: one MBConv
+    block, the run csrc/mbconv_umma.cu executes as one kernel.  expand=False: DW -> PW only (the
+    backbone's first block, expand ratio 1)."""
+    rng = np.random.default_rng(seed)
+    zp_in = -7
+    g = _empty_graph(h, w, cin, zp_in)
+    x = g.input
+    if expand:
+        x = g._pw(x, cexp, True, 'mb.expand')
+        _set_pw(rng, g, g.ops[-1], cin, cexp, zp_in, -128, True)
+        zp_mid = -128
+    else:
+        assert cexp == cin
+        zp_mid = zp_in
+    d = g._dw(x, k, stride, True, 'mb.dw')
+    _set_dw(rng, g, g.ops[-1], zp_mid, -120, True)
+    if residual:
+        assert stride == 1 and cin == cout and expand
+    o = g._pw(d, cout, False, 'mb.project', residual=g.input if residual else -1)
+    op = g.ops[-1]
+    _set_pw(rng, g, op, cexp, cout, -120, 5 if residual else 9, False)
+    if residual:
+        q = op.q
+        q['conv_zp_out'] = 5
+        q['zp_out'] = -3
+        q['res_zp'] = zp_in
+        q['add_mult'], q['add_shift'] = [int(0.61 * (1 << 20)), int(0.83 * (1 << 20))], 20
+        q['act_lo'], q['act_hi'] = -128, 127
+        g.tensors[o].zp = -3
+    return g
+
+
 def random_input(g, B, seed=1):
     """(logical int8 [B,h,w,c], padded int8 [B,h,w,c_p] with the zero point in the pad)."""
     t = g.tensors[g.input]

@@ -205,3 +205,71 @@ def test_fused_bifpn_node_with_add_tree(h, w, c, odd, B):
     g = MG.node_graph(h, w, c, n_in=3, seed=h * 10 + c + 1, odd=odd, tree=True)
     check(g, B)
     assert list(MG.run_gpu.last_plan)[-4:] == [4, 0, 0, 0]
+
+
+# ---- fused MBConv block (csrc/mbconv_umma.cu) -----------------------------------------------------
+
+# every block shape of EfficientDet-Lite0 / 1 / 2 (channels, kernel, stride; maps shrunk where the
+# full size adds nothing but time) plus odd sizes, tile tails and two-tile cases
+MBCONV_SHAPES = [
+    # h, w, cin, cexp, cout, k, s, residual, B
+    (24, 24, 16, 96, 24, 3, 2, False, 2),       # b2.0
+    (160, 160, 16, 96, 24, 3, 2, False, 1),     # b2.0 at full size: 2-D tiles, right / bottom tails
+    (20, 20, 24, 144, 24, 3, 1, True, 2),       # b2.1
+    (80, 80, 24, 144, 24, 3, 1, True, 1),
+    (22, 26, 24, 144, 40, 5, 2, False, 2),      # b3.0
+    (80, 80, 24, 144, 40, 5, 2, False, 1),
+    (40, 40, 40, 240, 40, 5, 1, True, 2),       # b3.1
+    (40, 40, 40, 240, 80, 3, 2, False, 2),      # b4.0
+    (20, 20, 80, 480, 80, 3, 1, True, 2),       # b4.1
+    (20, 20, 80, 480, 112, 5, 1, False, 2),     # b5.0
+    (20, 20, 112, 672, 112, 5, 1, True, 2),     # b5.1
+    (20, 20, 112, 672, 192, 5, 2, False, 2),    # b6.0
+    (10, 10, 192, 1152, 192, 5, 1, True, 3),    # b6.1
+    (10, 10, 192, 1152, 320, 3, 1, False, 3),   # b7.0: Cout 320 = two N halves
+    (24, 24, 48, 288, 48, 5, 1, True, 1),       # Lite2 widths
+    (14, 14, 120, 720, 120, 5, 1, True, 2),
+    (14, 14, 120, 720, 208, 5, 2, False, 2),
+    (7, 7, 208, 1248, 208, 5, 1, True, 2),
+    (7, 7, 208, 1248, 352, 3, 1, False, 2),     # Lite2 b7.0: Cout 352
+    (12, 12, 88, 528, 88, 3, 1, True, 2),
+    (17, 13, 24, 144, 24, 3, 1, True, 3),       # odd sizes
+    (17, 13, 24, 144, 40, 5, 2, False, 3),
+    (33, 31, 16, 96, 24, 3, 2, False, 1),
+    (9, 11, 40, 240, 40, 5, 1, True, 2),
+    (5, 5, 80, 480, 80, 3, 1, True, 4),
+    (3, 3, 192, 1152, 192, 5, 1, True, 5),
+    (1, 1, 16, 96, 16, 3, 1, True, 2),
+]
+
+
+@pytest.mark.parametrize('h,w,cin,cexp,cout,k,s,res,B', MBCONV_SHAPES)
+def test_fused_mbconv_block(h, w, cin, cexp, cout, k, s, res, B):
+    g = MG.mbconv_graph(h, w, cin, cexp, cout, k, s, residual=res, seed=h * 100 + cin + k)
+    check(g, B)
+    assert list(MG.run_gpu.last_plan) == [3, 0, 0], 'expand -> depthwise -> project must run as one kernel'
+
+
+@pytest.mark.parametrize('h,w,c,cout,k,s,B', [(160, 160, 32, 16, 3, 1, 1), (96, 70, 32, 16, 3, 1, 2), (80, 80, 16, 24, 5, 2, 1),
+                                              (67, 91, 32, 32, 3, 2, 2)])
+def test_fused_mbconv_without_expand(h, w, c, cout, k, s, B):
+    """The backbone's first block (expand ratio 1): depthwise -> project on a map too large for the
+    fused node kernel."""
+    g = MG.mbconv_graph(h, w, c, c, cout, k, s, seed=h + c, expand=False)
+    check(g, B)
+    assert list(MG.run_gpu.last_plan) == [2, 0]
+
+
+def test_mbconv_unfused_path_still_matches():
+    """VBT_MBCONV=0 runs the same blocks op by op (the kernels the fused one replaced)."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    code = ('import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); import test_gpu_ops as T; '
+            'import micrograph as MG\n'
+            'for (h, w, cin, cexp, cout, k, s, res, B) in T.MBCONV_SHAPES[::4]:\n'
+            '    T.check(MG.mbconv_graph(h, w, cin, cexp, cout, k, s, residual=res, seed=h), B)\n'
+            '    assert list(MG.run_gpu.last_plan) == [1, 1, 1]\n' % (os.path.dirname(here), here))
+    r = subprocess.run([sys.executable, '-c', code], env=dict(os.environ, VBT_MBCONV='0'), capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]

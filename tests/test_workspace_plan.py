@@ -1,10 +1,12 @@
 """Host-side planning of the layer program (vbt_b200/effdet.py), on the CPU:
-* the workspace plan never lets a tensor written by a fused [[ADD ->] ADD ->] DW3x3 -> PW run alias a
-  tensor the run reads -- the fused kernel's CTAs write the output while other CTAs still read the
+* the workspace plan never lets a tensor written by a fused [[ADD ->] ADD ->] DW3x3 -> PW run, or by a
+  fused MBConv block ([expand ->] depthwise -> project), alias a tensor the run reads -- the fused kernel's CTAs write the output while other CTAs still read the
   inputs (the aliasing the library re-checks in vbt_model_create);
 * liveness reuse stays safe for the single ops too (an op's output never overlaps its own inputs,
   nor any tensor that is still to be read later);
 * head chains are independent branches with private memory."""
+import re
+
 import pytest
 
 from vbt_b200 import effdet as E
@@ -45,8 +47,12 @@ def test_fused_runs_never_alias_their_inputs(variant):
                         continue
                     a0, a1 = _span(g, t)
                     assert o1 <= a0 or a1 <= o0, (variant, g.ops[i].name, g.ops[j].name)
-    # every BiFPN node and every head stage is a run: cells * 8 nodes + 5 levels * 2 nets * 4 stages
-    assert n_runs == g.cells * 8 + 40
+    # every BiFPN node and every head stage is a run: cells * 8 nodes + 5 levels * 2 nets * 4 stages;
+    # and every MBConv block of the backbone is one (16 / 21 / 21 blocks)
+    n_blocks = sum(1 for op in g.ops if re.fullmatch(r'b\d+\.\d+\.dw', op.name))
+    assert n_blocks == {'lite0': 16, 'lite1': 21, 'lite2': 21}[variant]
+    assert len(E.mbconv_runs(g)) == n_blocks
+    assert n_runs == g.cells * 8 + 40 + n_blocks
 
 
 @pytest.mark.parametrize('variant', ['lite0', 'lite2'])

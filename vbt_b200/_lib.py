@@ -48,6 +48,7 @@ PROTOTYPES = {
     'vbt_model_destroy': (None, [_P]),
     'vbt_model_info': (_I, [_P, C.POINTER(C.c_longlong)]),
     'vbt_model_plan': (_I, [_P, _P]),
+    'vbt_model_plan_kinds': (_I, [_P, _P]),
     'vbt_detect': (_I, [_P, _P, _I, _P, _SZ, _P, _P, _P]),
     'vbt_model_profile': (_I, [_P, _I]),
     'vbt_model_op_times': (_I, [_P, _P, C.POINTER(C.c_longlong)]),

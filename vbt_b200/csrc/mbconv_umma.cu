@@ -1,0 +1,597 @@
+// Fused MBConv block:  1x1 expand (ReLU6) -> depthwise 3x3 / 5x5, stride 1 / 2 (ReLU6) -> 1x1 project
+// [+ residual], ONE kernel per block; the 6x expanded tensor and the depthwise output never reach HBM.
+//
+// replaces: the CONV_2D 1x1 -> DEPTHWISE_CONV_2D -> CONV_2D 1x1 [-> ADD] quadruples of the
+// EfficientNet-Lite backbone inside tflite_runtime's signature_fn(images=...) (odt.py:58-61); SURVEY.md
+// 2.4 K3 / appendix A.2: 16 / 21 / 21 blocks in Lite0 / 1 / 2, 86 % of the network's MACs and (unfused)
+// 27.9 of its 35 M activation elements per frame.
+//
+// One CTA = one frame x one TH x TW tile of OUTPUT pixels, all channels.  The expanded channels are
+// walked in chunks of 32 (one tcgen05 N = 32 column block = two 16-channel groups):
+//   fill     the tile's input window (halo included) -> shared-memory planes, one per 16-channel
+//            group: [group][phase][position][16 B], position = ly * PWo + lx.  Stride 2 splits the
+//            window into its four (row, column) parity phases, so that every depthwise tap is a pure
+//            shift inside one phase plane.
+//   per chunk c (weights: ONE bulk copy of a host-prepared image, three buffers deep):
+//     E   expand GEMM  D_E[window positions, 32] = in planes x Wexp_c^T      (tcgen05.mma kind::i8,
+//         accumulators in TMEM), issued one chunk ahead so that it runs under the previous chunk's
+//         depthwise
+//     EE  epilogue: requantise + ReLU6 -> the chunk's expanded planes (same geometry as the input
+//         planes); positions outside the image get the expanded tensor's zero point (TF SAME
+//         pads the depthwise INPUT, i.e. the expanded tensor)
+//     DW  depthwise on the SIMT pipes, straight out of the planes: a thread owns one output position
+//         and 16 channels; per tap one 128-bit shared load + 16 dp4a against pre-masked weight words
+//         (the weight of channel c in byte c % 4, zeros elsewhere: no unpacking), requantise + ReLU6
+//         -> two "middle" planes = the K-major A operand of the project GEMM.  (The tensor-pipe form
+//         of csrc/dw_umma.cu -- block-diagonal tap matrices -- was built first and measured: every
+//         M128 N32 K32 tap MMA occupies the pipe ~100 cycles, 2,500 cycles per chunk for 5x5, on the
+//         same pipe the two GEMMs need; the dp4a form takes ~1,100 and runs beside them.)
+//     P   project GEMM  D_P[output positions, Cout] += middle planes x Wproj[:, chunk]^T, the
+//         accumulator staying in TMEM over all chunks
+//   final   D_P -> bias, requantise, quantised residual add (the block input, still in the input
+//           planes), store.
+// MMAs are issued by one ELECTED lane of a warp-uniform region: issuing from `if (tid == 0)` makes
+// ptxas wrap every UTCIMMA in an ELECT / R2UR / BRA.U.ANY loop (~100 cycles each, measured).
+#include "model.cuh"
+#include "requant.cuh"
+
+namespace {
+
+using vbt::OpRecord;
+
+constexpr int kThreads = 256;      // 8 warps: warp w owns TMEM lanes 32 * (w % 4) .., 16-channel half w / 4
+constexpr int kWBuf = 3;           // weight-image buffers
+constexpr int kMaxCout = 352;
+
+struct MbArgs {
+  const int8_t* in; int8_t* out;
+  const unsigned char* img;                  // [n_chunks][img_stride] weight images (effdet.mbconv_images)
+  const int32_t* pj_bias; const float* pj_mult;
+  int B, H, W, Ho, Wo;                       // depthwise input (= block input) size, output size
+  int cin_p, g_in, ge_in, cout_p, n_chunks;
+  int K, S, pad_top, pad_left, halo;
+  int has_expand, has_res;
+  int TH, TW, tiles_x, PWo, rows_alloc, plane_pos, n_phase, m_total, n_win_tiles, n_out_tiles;
+  uint32_t inv_pwo, inv_plane, inv_gin;      // ceil(2^32 / d)
+  int zp_fill;                               // zero point of the depthwise input (padding value)
+  vbt::Requant ex_rq, dw_rq, pj_rq;
+  int pj_zp, res_zp, add_mult0, add_mult1, add_shift, zp_final, lo, hi;
+  int img_stride, img_bytes, off_taps, off_wproj, off_consts;
+  int tmem_cols, col_pj;
+  uint32_t sm_exp, sm_mid, sm_wbuf, in_gstride, exp_gstride, mid_gstride;   // bytes
+  long long* dbg;                            // VBT_MB_DBG=1: cycle counters of CTA (0,0), threads 0 and 64
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate));
+}
+// Warp-uniform issue: the whole warp runs the (uniform) descriptor arithmetic, one elected lane issues.
+// Issuing from a divergent `if (tid == 0)` makes ptxas wrap every UTCIMMA in an ELECT / BRA.U.ANY loop
+// (its operands live in uniform registers and it cannot prove a one-lane region uniform): ~100 cycles
+// per instruction, measured.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0, lane = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %2;\n\t@px mov.s32 %1, 1;\n\tmov.s32 %0, rx;\n\t}\n"
+      : "+r"(lane), "+r"(pred) : "r"(0xffffffffu));
+  return pred;
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  for (long long spin = 0; !ok; ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (spin > (1LL << 24)) __trap();                 // a lost commit must not hang the GPU
+  }
+}
+__device__ __forceinline__ void st_shared16(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint4 ld_shared16(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, "
+      "%13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+
+#define MB_TICK(i)                                                        \
+  do {                                                                   \
+    if (dbg_on) { const long long now__ = clock64(); dbg_acc[i] += now__ - dbg_t; dbg_t = now__; } \
+  } while (0)
+
+// 16 accumulators (bias included) -> 16 int8; the packed / plain requantisation chosen once per call
+__device__ __forceinline__ uint4 requant16r(const int (&v)[16], const vbt::Requant& rq, const float (&m)[16]) {
+  uint32_t p[4];
+  if (rq.fast) {
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4)
+      p[w4] = rq.pack4t<true>(v[w4 * 4], v[w4 * 4 + 1], v[w4 * 4 + 2], v[w4 * 4 + 3], m[w4 * 4], m[w4 * 4 + 1], m[w4 * 4 + 2], m[w4 * 4 + 3]);
+  } else {
+#pragma unroll
+    for (int w4 = 0; w4 < 4; ++w4)
+      p[w4] = rq.pack4t<false>(v[w4 * 4], v[w4 * 4 + 1], v[w4 * 4 + 2], v[w4 * 4 + 3], m[w4 * 4], m[w4 * 4 + 1], m[w4 * 4 + 2], m[w4 * 4 + 3]);
+  }
+  return make_uint4(p[0], p[1], p[2], p[3]);
+}
+// 16 int32 / float constants of this thread's channel half from the chunk image
+__device__ __forceinline__ void load16(uint32_t addr, int (&o)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = ld_shared16(addr + j * 16);
+    o[j * 4] = (int)v.x; o[j * 4 + 1] = (int)v.y; o[j * 4 + 2] = (int)v.z; o[j * 4 + 3] = (int)v.w;
+  }
+}
+__device__ __forceinline__ void load16(uint32_t addr, float (&o)[16]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint4 v = ld_shared16(addr + j * 16);
+    o[j * 4] = __uint_as_float(v.x); o[j * 4 + 1] = __uint_as_float(v.y);
+    o[j * 4 + 2] = __uint_as_float(v.z); o[j * 4 + 3] = __uint_as_float(v.w);
+  }
+}
+
+template <int K, int S>
+__global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) int32_t sPjBias[kMaxCout];
+  __shared__ __align__(16) float sPjMult[kMaxCout];
+  constexpr int ss = S - 1;
+  constexpr int taps = K * K;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+  const int tile = blockIdx.x, b = blockIdx.y;
+  const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+  const int oy0 = ty * a.TH, ox0 = tx * a.TW;
+  const int ey0 = oy0 * S - a.pad_top, ex0 = ox0 * S - a.pad_left;   // window origin in input coordinates
+  const uint32_t s_in = smem_u32(smem), s_exp = s_in + a.sm_exp, s_mid = s_in + a.sm_mid;
+  const uint32_t s_wbuf = s_in + a.sm_wbuf;
+  const int n_chunks = a.n_chunks;
+  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 64);
+  long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long dbg_t = dbg_on ? clock64() : 0;
+
+  // ---- prologue: model constants and CTA-private state only --------------------------------------
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(
+                     smem_u32(&tmem_base_s)), "r"((uint32_t)a.tmem_cols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
+  }
+  if (tid == 0) {
+    for (int i = 0; i < kWBuf; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_w[i])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_e)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+  }
+  for (int i = tid; i < a.cout_p; i += kThreads) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
+  __syncthreads();                 // barriers initialised before anyone arms or polls them
+  auto load_image = [&](int c) {   // one thread: one bulk copy (TMA engine) of chunk c's weight image
+    const uint32_t bar = smem_u32(&bar_w[c % kWBuf]);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)a.img_bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                     "r"(s_wbuf + (uint32_t)(c % kWBuf) * a.img_stride),
+                 "l"(a.img + (size_t)c * a.img_stride), "r"((uint32_t)a.img_bytes), "r"(bar)
+                 : "memory");
+  };
+  if (tid == 64) load_image(0);
+  vbt::pdl_wait();
+  vbt::pdl_launch_dependents();
+
+  // ---- fill: the tile's input window -> planes --------------------------------------------------------
+  {
+    // with an expand conv the planes feed the expand GEMM (positions outside the image are never
+    // used: EE overrides them); without one they ARE the depthwise input: pad with the zero point
+    const uint32_t zpw = (uint32_t)(a.zp_fill & 0xff) * 0x01010101u;
+    const int G = a.has_expand ? a.g_in : 2;
+    const uint32_t base = a.has_expand ? s_in : s_exp;
+    const uint32_t gstride = a.has_expand ? a.in_gstride : a.exp_gstride;
+    const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
+    const int items = a.m_total * G;
+    for (int i = tid; i < items; i += kThreads) {
+      const int m = !a.has_expand ? (i >> 1) : (G == 1 ? i : (int)__umulhi((uint32_t)i, a.inv_gin));   // ceil(2^32 / 1) does not fit
+      const int g = i - m * G;                          // groups fastest: 16 B x G contiguous in global
+      const int ph = (int)__umulhi((uint32_t)m, a.inv_plane);
+      const int pos = m - ph * a.plane_pos;
+      const int ly = (int)__umulhi((uint32_t)pos, a.inv_pwo);
+      const int lx = pos - ly * a.PWo;
+      const int iy = ey0 + (ly << ss) + (ph >> ss), ix = ex0 + (lx << ss) + (ph & ss);
+      const uint32_t dst = base + (uint32_t)g * gstride + (uint32_t)m * 16;
+      const bool inside = iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && ly < a.rows_alloc;
+      if (inside && g < a.g_in) {
+        const int8_t* src = fin + ((size_t)iy * a.W + ix) * a.cin_p + g * 16;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src));
+      } else if (!a.has_expand) {
+        st_shared16(dst, make_uint4(zpw, zpw, zpw, zpw));
+      }
+    }
+  }
+  // which of this thread's window positions (row of every window tile) lie inside the image
+  uint32_t inside_mask = 0;
+  for (int wt = 0; wt < a.n_win_tiles; ++wt) {
+    const int m = wt * 128 + row;
+    const int ph = (int)__umulhi((uint32_t)m, a.inv_plane);
+    const int pos = m - ph * a.plane_pos;
+    const int ly = (int)__umulhi((uint32_t)pos, a.inv_pwo);
+    const int lx = pos - ly * a.PWo;
+    const int iy = ey0 + (ly << ss) + (ph >> ss), ix = ex0 + (lx << ss) + (ph & ss);
+    if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) inside_mask |= 1u << wt;
+  }
+  asm volatile("cp.async.commit_group;\n");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+  // the issuing warps see their own index and the TMEM base as warp-uniform values
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  MB_TICK(0);                                          // prologue + fill
+
+  // D = S32, A = B = signed int8, K-major, M = 128, N = 32
+  const uint32_t idesc32 = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  // Descriptors are built once; inside the loops a start address moves by adding (bytes >> 4) to the
+  // descriptor's low word (the 14-bit address field never overflows: everything lies below 256 KB).
+  // Two issuing warps: warp 0 owns P, warp 1 owns E, one elected lane each.
+  const uint64_t e_adesc = umma_desc(s_in, a.in_gstride, 128);
+  const uint64_t e_bdesc = umma_desc(s_wbuf, 128, (uint32_t)a.ge_in * 128);
+  const uint32_t e_kstep = (2 * a.in_gstride) >> 4;
+  auto issue_expand = [&](int c) {                     // one elected lane of warp 1
+    const uint64_t bd = e_bdesc + (uint64_t)(((uint32_t)(c % kWBuf) * a.img_stride) >> 4);
+    const int ksteps = a.ge_in >> 1;
+    for (int wt = 0; wt < a.n_win_tiles; ++wt) {
+      const uint64_t ad = e_adesc + (uint64_t)(wt * 128);
+      const uint32_t d = tmem_u + (uint32_t)wt * 32;
+      for (int k2 = 0; k2 < ksteps; ++k2)
+        umma_i8(d, ad + (uint64_t)(k2 * e_kstep), bd + (uint64_t)(k2 * 16), idesc32, k2 > 0 ? 1u : 0u);
+    }
+    umma_commit(smem_u32(&bar_e));
+  };
+  if (warp_u == 1 && a.has_expand) {
+    mbar_wait(smem_u32(&bar_w[0]), 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+    if (elect_one()) issue_expand(0);
+  }
+
+  const uint64_t pj_adesc = umma_desc(s_mid, a.mid_gstride, 128);
+  const uint64_t pj_bdesc = umma_desc(s_wbuf + a.off_wproj, 128, 256);
+  const int pj_n0 = a.cout_p <= 256 ? a.cout_p : (a.cout_p / 32) * 16;
+  const uint32_t pj_id0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(pj_n0 >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t pj_id1 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)((a.cout_p - pj_n0) >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t zpw = (uint32_t)(a.zp_fill & 0xff) * 0x01010101u;
+  const uint32_t mid_buf = 2 * a.mid_gstride;          // bytes of one middle-plane buffer (two groups)
+  uint32_t par_e = 0;
+  for (int c = 0; c < n_chunks; ++c) {
+    const uint32_t wb = s_wbuf + (uint32_t)(c % kWBuf) * a.img_stride;
+    const uint32_t consts = wb + a.off_consts;
+    // Buffer reuse: weight buffer (c + 1) % 3 last held chunk c - 2 and middle buffer c & 1 was last
+    // read by P(c - 2): both are free once P(c - 2) has completed (E(c - 2) did long ago).
+    if (warp_u == 2) {
+      if (c >= 2) mbar_wait(smem_u32(&bar_p[c & 1]), (uint32_t)(((c - 2) >> 1) & 1));
+      if (c + 1 < n_chunks && elect_one()) load_image(c + 1);
+    }
+    mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));     // image c visible to every thread
+    MB_TICK(1);
+    // ---- EE: expand epilogue -> the chunk's expanded planes -------------------------------------------
+    if (a.has_expand) {
+      if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
+      __syncthreads();
+      par_e ^= 1;
+      asm volatile("tcgen05.fence::after_thread_sync;\n");
+      MB_TICK(2);
+      int eb[16];
+      float em[16];
+      load16(consts + half * 64, eb);
+      load16(consts + 128 + half * 64, em);
+      for (int wt = 0; wt < a.n_win_tiles; ++wt) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + (uint32_t)(wt * 32 + half * 16), v);
+        uint4 o = make_uint4(zpw, zpw, zpw, zpw);
+        if ((inside_mask >> wt) & 1u) {
+          int acc[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = (int)v[j] + eb[j];
+          o = requant16r(acc, a.ex_rq, em);
+        }
+        st_shared16(s_exp + (uint32_t)half * a.exp_gstride + (uint32_t)(wt * 128 + row) * 16, o);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;\n");
+    }
+    MB_TICK(3);
+    __syncthreads();               // expanded planes complete (and free of the previous chunk's readers)
+    MB_TICK(4);
+    // ---- E(c + 1): runs on the tensor pipe while the SIMT pipes do this chunk's depthwise -----------------
+    if (warp_u == 1 && a.has_expand && c + 1 < n_chunks) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n");
+      mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
+      if (elect_one()) issue_expand(c + 1);
+    }
+    MB_TICK(5);
+    // ---- DW + DE: depthwise straight out of the planes -> middle planes (buffer c & 1) -------------------
+    {
+      int db[16];
+      float dm[16];
+      load16(consts + 256 + half * 64, db);
+      load16(consts + 384 + half * 64, dm);
+      const uint32_t wbase = wb + a.off_taps + (uint32_t)half * 64;
+      for (int t = 0; t < a.n_out_tiles; ++t) {
+        const uint32_t xbase = s_exp + (uint32_t)half * a.exp_gstride + (uint32_t)(t * 128 + row) * 16;
+        int acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = db[j];
+#pragma unroll
+        for (int ky = 0; ky < K; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx < K; ++kx) {
+            // phase plane + shift inside it, in 16-byte positions
+            const uint32_t delta = (uint32_t)((((ky & ss) << ss) | (kx & ss)) * a.plane_pos + (ky >> ss) * a.PWo + (kx >> ss));
+            const uint4 x = ld_shared16(xbase + delta * 16);
+            const uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 w = ld_shared16(wbase + (uint32_t)((ky * K + kx) * 128 + j * 16));
+              acc[j * 4 + 0] = __dp4a((int)xs[j], (int)w.x, acc[j * 4 + 0]);
+              acc[j * 4 + 1] = __dp4a((int)xs[j], (int)w.y, acc[j * 4 + 1]);
+              acc[j * 4 + 2] = __dp4a((int)xs[j], (int)w.z, acc[j * 4 + 2]);
+              acc[j * 4 + 3] = __dp4a((int)xs[j], (int)w.w, acc[j * 4 + 3]);
+            }
+          }
+        }
+        st_shared16(s_mid + (uint32_t)(c & 1) * mid_buf + (uint32_t)half * a.mid_gstride + (uint32_t)(t * 128 + row) * 16,
+                    requant16r(acc, a.dw_rq, dm));
+      }
+    }
+    MB_TICK(8);
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;\n");
+    __syncthreads();
+    MB_TICK(9);
+    // ---- P(c): project GEMM, accumulating over chunks ---------------------------------------------------
+    if (warp_u == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n");
+      if (elect_one()) {
+        const uint64_t bd = pj_bdesc + (uint64_t)(((uint32_t)(c % kWBuf) * a.img_stride) >> 4);
+        for (int t = 0; t < a.n_out_tiles; ++t) {
+          const uint64_t ad = pj_adesc + (uint64_t)((((uint32_t)(c & 1) * mid_buf) >> 4) + t * 128);
+          const uint32_t d0 = tmem_u + (uint32_t)(a.col_pj + t * a.cout_p);
+          umma_i8(d0, ad, bd, pj_id0, c > 0 ? 1u : 0u);
+          if (pj_n0 < a.cout_p) umma_i8(d0 + (uint32_t)pj_n0, ad, bd + (uint64_t)((pj_n0 / 8) * 16), pj_id1, c > 0 ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&bar_p[c & 1]));
+      }
+    }
+    MB_TICK(10);
+  }
+
+  // ---- final epilogue: bias, requantise, residual, store ----------------------------------------------------
+  if (warp == 0) mbar_wait(smem_u32(&bar_p[(n_chunks - 1) & 1]), (uint32_t)(((n_chunks - 1) >> 1) & 1));
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
+  for (int t = 0; t < a.n_out_tiles; ++t) {
+    const int q = t * 128 + row;
+    const int ly = (int)__umulhi((uint32_t)q, a.inv_pwo);
+    const int lx = q - ly * a.PWo;
+    const int oy = oy0 + ly, ox = ox0 + lx;
+    const bool valid = ly < a.TH && lx < a.TW && oy < a.Ho && ox < a.Wo;
+    int8_t* o = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.cout_p;
+    // residual: the block input at the same pixel (stride 1), still in the input planes
+    const uint32_t rpos = (uint32_t)((ly + a.pad_top) * a.PWo + lx + a.pad_left) * 16;
+    for (int c0 = half * 16; c0 < a.cout_p; c0 += 32) {
+      uint32_t v[16];
+      tmem_ld16(tmem + lane_base + (uint32_t)(a.col_pj + t * a.cout_p + c0), v);
+      if (!valid) continue;
+      uint32_t packed[4];
+      uint4 rv = make_uint4(0, 0, 0, 0);
+      if (a.has_res) rv = ld_shared16(s_in + (uint32_t)(c0 >> 4) * a.in_gstride + rpos);
+      const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+      for (int w4 = 0; w4 < 4; ++w4) {
+        const int4 bq = *reinterpret_cast<const int4*>(sPjBias + c0 + w4 * 4);
+        const float4 mq = *reinterpret_cast<const float4*>(sPjMult + c0 + w4 * 4);
+        if (!a.has_res) {
+          packed[w4] = a.pj_rq.pack4((int)v[w4 * 4 + 0] + bq.x, (int)v[w4 * 4 + 1] + bq.y, (int)v[w4 * 4 + 2] + bq.z,
+                                     (int)v[w4 * 4 + 3] + bq.w, mq.x, mq.y, mq.z, mq.w);
+        } else {
+          const int bs[4] = {bq.x, bq.y, bq.z, bq.w};
+          const float ms[4] = {mq.x, mq.y, mq.z, mq.w};
+          int y[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            y[j] = a.pj_rq((int)v[w4 * 4 + j] + bs[j], ms[j]);
+            const int r = (int)(int8_t)(rw[w4] >> (8 * j));
+            const int s = (y[j] - a.pj_zp) * a.add_mult0 + (r - a.res_zp) * a.add_mult1 + round;
+            y[j] = clampi((s >> a.add_shift) + a.zp_final, a.lo, a.hi);
+          }
+          packed[w4] = vbt::pack4_s8(y[0], y[1], y[2], y[3]);
+        }
+      }
+      *reinterpret_cast<uint4*>(o + c0) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    }
+  }
+  MB_TICK(11);
+  if (dbg_on)
+    for (int i = 0; i < 12; ++i) a.dbg[(tid ? 12 : 0) + i] = dbg_acc[i];
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem), "r"((uint32_t)a.tmem_cols));
+  }
+}
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+namespace vbt {
+
+// ops: [expand PW (or null)] -> DW -> project PW (n_in == 2: + residual = the expand's input).
+// *taken = false leaves the run to the single-op kernels.
+int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& dw, const OpRecord& pj,
+                       const int8_t* in, int8_t* out, int B, cudaStream_t st, bool* taken) {
+  static const bool enabled = [] { const char* e = getenv("VBT_MBCONV"); return !(e && e[0] == '0'); }();
+  *taken = false;
+  if (!enabled || dw.mb[0] <= 0) return VBT_OK;
+  MbArgs a;
+  a.in = in; a.out = out;
+  a.img = m->dev_data + (size_t)(dw.mb[0] - 1) * 256;
+  a.img_stride = dw.mb[1]; a.n_chunks = dw.mb[2];
+  a.pj_bias = reinterpret_cast<const int32_t*>(m->dev_data + pj.bias_off);
+  a.pj_mult = reinterpret_cast<const float*>(m->dev_data + pj.scale_off);
+  a.B = B; a.H = dw.h_in; a.W = dw.w_in; a.Ho = dw.h_out; a.Wo = dw.w_out;
+  a.has_expand = ex != nullptr;
+  a.cin_p = ex ? ex->cin_p : dw.cin_p;
+  a.g_in = a.cin_p / 16; a.ge_in = (a.g_in + 1) / 2 * 2;
+  a.cout_p = pj.cout_p;
+  a.K = dw.k; a.S = dw.stride; a.pad_top = dw.pad_top; a.pad_left = dw.pad_left;
+  a.halo = (dw.k - 1) >> (dw.stride - 1);
+  a.has_res = pj.n_in == 2;
+  if (a.cout_p > kMaxCout || a.cout_p % 16 || a.ge_in > 16 || (dw.k != 3 && dw.k != 5) || (dw.stride != 1 && dw.stride != 2)) return VBT_OK;
+  if (!ex && (a.n_chunks != 1 || a.has_res)) return VBT_OK;
+  if (a.has_res && (dw.stride != 1 || !ex || pj.cout_p != ex->cin_p)) return VBT_OK;
+  a.zp_fill = dw.zp_in[0];
+  if (ex) a.ex_rq = Requant(ex->zp_out, ex->act_lo, ex->act_hi, ex->requant_fast);
+  a.dw_rq = Requant(dw.zp_out, dw.act_lo, dw.act_hi, dw.requant_fast);
+  a.pj_rq = a.has_res ? Requant(pj.zp_out, -128, 127) : Requant(pj.zp_out, pj.act_lo, pj.act_hi, pj.requant_fast);
+  a.pj_zp = pj.zp_out; a.res_zp = pj.zp_in[1];
+  a.add_mult0 = pj.add_mult[0]; a.add_mult1 = pj.add_mult[1]; a.add_shift = pj.add_shift;
+  a.zp_final = pj.zp_in[2]; a.lo = pj.act_lo; a.hi = pj.act_hi;
+  // chunk image layout (effdet.mbconv_image_layout)
+  const int sz_wexp = ex ? 32 * a.ge_in * 16 : 0;
+  a.off_taps = sz_wexp;
+  a.off_wproj = a.off_taps + dw.k * dw.k * 128;      // [k*k][32] pre-masked weight words
+  a.off_consts = a.off_wproj + a.cout_p * 32;
+  a.img_bytes = a.off_consts + 512;
+  if (round_up(a.img_bytes, 128) != a.img_stride) {
+    set_error("vbt_detect: MBConv weight image stride %d does not match the layout (%d)", a.img_stride, round_up(a.img_bytes, 128));
+    return VBT_EFORMAT;
+  }
+  // ---- tile choice: TH x TW output pixels per CTA; one or two 128-position output tiles ---------------
+  static const int env_tw = [] { const char* e = getenv("VBT_MB_TW"); return e ? atoi(e) : 0; }();
+  static const int env_ot = [] { const char* e = getenv("VBT_MB_OT"); return e ? atoi(e) : 0; }();
+  long long best = -1;
+  int bTH = 0, bTW = 0;
+  for (int ot = 1; ot <= 2; ++ot) {
+    if (env_ot && ot != env_ot) continue;
+    for (int tw = 4; tw <= a.Wo + 3; tw += 2) {
+      const int TW = std::min(tw, a.Wo);
+      if (env_tw && TW != std::min(env_tw, a.Wo)) continue;
+      const int PWo = TW + a.halo;
+      const int TH = std::min(a.Ho, ot * 128 / PWo);
+      if (TH < 1) continue;
+      const int n_out = (TH * PWo + 127) / 128;
+      const int rows = TH + a.halo;
+      const int plane = round_up(std::max(rows * PWo, n_out * 128 + a.halo * PWo + a.halo), 8);
+      const int n_win = (dw.stride * dw.stride * plane + 127) / 128;
+      const int cols = (ex ? n_win * 32 : 0) + n_out * a.cout_p;
+      if (cols > 512 || n_win > 8) continue;
+      int cols_p = 32;
+      while (cols_p < cols) cols_p <<= 1;
+      const size_t sm = (size_t)(ex ? a.ge_in : 0) * n_win * 2048 + (size_t)2 * n_win * 2048 + (size_t)4 * n_out * 2048 +
+                        (size_t)kWBuf * a.img_stride;
+      if (sm > 200 * 1024) continue;
+      const int per_sm = std::max(1, std::min(std::min((int)(226 * 1024 / (sm + 4096)), 512 / cols_p), 2));
+      const long long ctas = (long long)B * ((a.Ho + TH - 1) / TH) * ((a.Wo + TW - 1) / TW);
+      const long long waves = (ctas + 148LL * per_sm - 1) / (148LL * per_sm);
+      // per-CTA cost model (~cycles): fill + per chunk (expand epilogue per window tile, SIMT depthwise
+      // per output tile, barriers) + final epilogue; two CTAs sharing an SM share its issue slots
+      const long long per_chunk = 500 + (ex ? 420LL * n_win : 0) + (long long)n_out * (48LL * dw.k * dw.k + 250);
+      const long long cta = 2500 + 40LL * n_win * a.ge_in + a.n_chunks * per_chunk + (long long)n_out * a.cout_p * 8;
+      const long long cost = waves * cta * (per_sm == 2 ? 17 : 10) / 10;
+      if (best < 0 || cost < best) { best = cost; bTH = TH; bTW = TW; }
+    }
+  }
+  if (best < 0) return VBT_OK;
+  a.TH = bTH; a.TW = bTW;
+  a.PWo = a.TW + a.halo;
+  a.tiles_x = (a.Wo + a.TW - 1) / a.TW;
+  const int tiles_y = (a.Ho + a.TH - 1) / a.TH;
+  a.n_out_tiles = (a.TH * a.PWo + 127) / 128;
+  a.rows_alloc = a.TH + a.halo;
+  a.plane_pos = round_up(std::max(a.rows_alloc * a.PWo, a.n_out_tiles * 128 + a.halo * a.PWo + a.halo), 8);
+  a.n_phase = dw.stride * dw.stride;
+  a.m_total = a.n_phase * a.plane_pos;
+  a.n_win_tiles = (a.m_total + 127) / 128;
+  a.inv_pwo = (uint32_t)((0x100000000ULL + a.PWo - 1) / a.PWo);
+  a.inv_plane = (uint32_t)((0x100000000ULL + a.plane_pos - 1) / a.plane_pos);
+  a.inv_gin = a.g_in > 1 ? (uint32_t)((0x100000000ULL + a.g_in - 1) / a.g_in) : 0u;
+  a.in_gstride = (uint32_t)a.n_win_tiles * 2048;
+  a.exp_gstride = (uint32_t)a.n_win_tiles * 2048;
+  a.mid_gstride = (uint32_t)a.n_out_tiles * 2048;
+  a.sm_exp = (ex ? a.ge_in : 0) * a.in_gstride;
+  a.sm_mid = a.sm_exp + 2 * a.exp_gstride;
+  a.sm_wbuf = a.sm_mid + 4 * a.mid_gstride;           // two middle buffers of two groups
+  size_t smem = (size_t)a.sm_wbuf + (size_t)kWBuf * a.img_stride;
+  a.col_pj = ex ? a.n_win_tiles * 32 : 0;
+  int cols = 32;
+  while (cols < a.col_pj + a.n_out_tiles * a.cout_p) cols <<= 1;
+  a.tmem_cols = cols;
+  if (cols > 512 || smem > 200 * 1024) return VBT_OK;
+  // never more CTAs per SM than TMEM can serve, so tcgen05.alloc never spins
+  smem = std::max(smem, (size_t)228 * 1024 / (512 / cols + 1));
+  void (*kern)(MbArgs) = dw.k == 3 ? (dw.stride == 1 ? mbconv_umma_kernel<3, 1> : mbconv_umma_kernel<3, 2>)
+                                   : (dw.stride == 1 ? mbconv_umma_kernel<5, 1> : mbconv_umma_kernel<5, 2>);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  static const bool dbg = [] { const char* e = getenv("VBT_MB_DBG"); return e && e[0] == '1'; }();
+  static long long* dbg_buf = nullptr;
+  a.dbg = nullptr;
+  if (dbg) {
+    if (!dbg_buf) cudaMalloc(&dbg_buf, 24 * sizeof(long long));
+    a.dbg = dbg_buf;
+  }
+  VBT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)(a.tiles_x * tiles_y), (unsigned)B), dim3(kThreads), smem, st, a));
+  if (dbg) {       // debugging aid, never inside a graph capture: cycle counters of CTA (0, 0)
+    long long h[24];
+    cudaStreamSynchronize(st);
+    cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    static const char* nm[12] = {"prologue+fill", "wait image", "wait E", "EE", "sync", "E issue", "-", "-",
+                                 "DW+DE", "fence+sync", "P issue", "final"};
+    fprintf(stderr, "[mbconv %dx%d cin_p %d k%d s%d cout_p %d chunks %d | TH %d TW %d win_tiles %d out_tiles %d grid %d x %d tmem %d smem %zu]\n",
+            a.H, a.W, a.cin_p, a.K, a.S, a.cout_p, a.n_chunks, a.TH, a.TW, a.n_win_tiles, a.n_out_tiles,
+            a.tiles_x * tiles_y, B, a.tmem_cols, smem);
+    for (int i = 0; i < 12; ++i) fprintf(stderr, "   %-14s t0 %8lld   t64 %8lld\n", nm[i], h[i], h[12 + i]);
+  }
+  *taken = true;
+  return VBT_OK;
+}
+
+}  // namespace vbt

@@ -161,8 +161,35 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
              pw_ok(m->ops[i + 2], m->ops[i + 1]);
     };
     m->fuse.assign(n, 1);
+    m->fuse_kind.assign(n, 0);
+    // MBConv blocks: [expand PW ->] DW -> project PW as one mbconv_umma kernel
+    static const bool mb_on = [] { const char* e = getenv("VBT_MBCONV"); return !(e && e[0] == '0'); }();
+    std::vector<char> in_mb(n, 0);
+    for (int i = 0; mb_on && i < n; ++i) {
+      const OpRecord& d = m->ops[i];
+      if (d.type != OP_DW || d.mb[0] <= 0) continue;
+      const int first = i + d.mb[3], last = i + 1;
+      if (first < 0 || first > i || last >= n || d.mb[3] < -1) continue;
+      const OpRecord& p = m->ops[last];
+      bool ok = p.type == OP_PW && p.in[0] == d.out && p.out_kind == 0 && d.out >= 0 && readers[d.out] == 1 &&
+                p.branch == d.branch && p.cin_p == d.cout_p &&
+                (size_t)(d.mb[0] - 1) * 256 + (size_t)d.mb[1] * d.mb[2] <= (size_t)hdr.data_bytes;
+      if (ok && first < i) {
+        const OpRecord& e = m->ops[first];
+        ok = e.type == OP_PW && e.n_in == 1 && e.out >= 0 && d.in[0] == e.out && readers[e.out] == 1 && e.out_kind == 0 &&
+             e.cout_p == d.cout_p && (p.n_in == 1 || p.in[1] == e.in[0]);
+      } else if (ok) {
+        ok = p.n_in == 1;
+      }
+      if (!ok || !disjoint(first, last)) continue;
+      m->fuse[first] = last - first + 1;
+      m->fuse_kind[first] = 1;
+      for (int j = first + 1; j <= last; ++j) m->fuse[j] = 0;
+      for (int j = first; j <= last; ++j) in_mb[j] = 1;
+    }
     for (int i = 0; i < n;) {
       const OpRecord& o = m->ops[i];
+      if (in_mb[i]) { i += 1; continue; }
       if (max_hw > 0 && o.type == OP_ADD && o.n_in == 2 && o.out >= 0 && readers[o.out] == 1 && i + 3 < n &&
           m->ops[i + 1].type == OP_ADD && m->ops[i + 1].n_in == 2 && m->ops[i + 1].branch == o.branch &&
           (m->ops[i + 1].in[0] == o.out || m->ops[i + 1].in[1] == o.out) && add_dw_pw(i + 1) &&
@@ -230,6 +257,12 @@ int vbt_model_info(const vbt_model* m, long long info[8]) {
 int vbt_model_plan(const vbt_model* m, int32_t* host_group_len) {
   VBT_REQUIRE(m && host_group_len, "vbt_model_plan: null pointer");
   for (size_t i = 0; i < m->ops.size(); ++i) host_group_len[i] = m->fuse[i];
+  return VBT_OK;
+}
+
+int vbt_model_plan_kinds(const vbt_model* m, int32_t* host_kind) {
+  VBT_REQUIRE(m && host_kind, "vbt_model_plan_kinds: null pointer");
+  for (size_t i = 0; i < m->ops.size(); ++i) host_kind[i] = m->fuse_kind[i];
   return VBT_OK;
 }
 

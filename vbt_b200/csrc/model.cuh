@@ -13,7 +13,7 @@ namespace vbt {
 // Blob layout (little endian):
 //   BlobHeader | OpRecord[n_ops] | data section (256-byte aligned offsets)
 constexpr uint32_t kBlobMagic = 0x4d544256u;  // "VBTM"
-constexpr int kBlobVersion = 10;
+constexpr int kBlobVersion = 11;
 
 struct BlobHeader {
   uint32_t magic;
@@ -76,7 +76,10 @@ struct OpRecord {
   int32_t branch;          // 0: trunk (program order); k > 0: head chain k, independent of the others
   int32_t requant_fast;    // 1: |acc * mult| < 2^15 - 256 for every possible input (Requant::pack4)
   int32_t pw_dtype;        // OP_PW inside a fused head stage: 0 int8 (kind::i8), 1 bf16 (kind::f16)
-  int32_t reserved[4];
+  // OP_DW inside an MBConv block the fused kernel can take (csrc/mbconv_umma.cu): weight-image offset
+  // in the data section / 256 + 1 (0: none), image stride in bytes, number of 32-channel chunks,
+  // index of the run's first op relative to this one (-1: expand conv in front, 0: none)
+  int32_t mb[4];
 };
 static_assert(sizeof(OpRecord) == 224, "op record layout");
 
@@ -106,6 +109,7 @@ struct vbt_model {
   // launch plan: fuse[i] = number of consecutive ops the launch starting at op i covers
   // ([ADD ->] DW3x3 -> PW on small maps run as one node_umma kernel), 0 for ops inside a group
   std::vector<int> fuse;
+  std::vector<int> fuse_kind;   // per launch start: 0 single op / fused node (node_umma.cu), 1 MBConv block (mbconv_umma.cu)
   // work counters of the persistent kernels' dynamic tile schedulers: 16 ints per (workspace, op),
   // all zero between launches (the last CTA of a launch puts them back).  One block of n_ops * 16
   // per workspace the model has been run on, so concurrent lanes never share a counter.

@@ -27,6 +27,8 @@ int launch_dw_umma(const vbt_model* m, const OpRecord& op, const int8_t* in, int
 int launch_node_umma(const vbt_model* m, const OpRecord* add0, const OpRecord* add, const OpRecord& dw,
                      const OpRecord& pw, const int8_t* const in[3], int8_t* out, long long out_batch_stride, int B,
                      cudaStream_t st, bool* taken);
+int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& dw, const OpRecord& pj,
+                       const int8_t* in, int8_t* out, int B, cudaStream_t st, bool* taken);
 }
 
 namespace {
@@ -519,7 +521,16 @@ int run_ops(vbt_model* m, const uint8_t* dev_in, int B, void* dev_workspace, int
     }
     // fused [ADD ->] DW3x3 -> PW group: one kernel; falls through to the single ops if declined
     int covered = 1;
-    if (m->fuse[oi] > 1) {
+    if (m->fuse[oi] > 1 && m->fuse_kind[oi] == 1) {
+      // MBConv block: [expand ->] depthwise -> project as one kernel (csrc/mbconv_umma.cu)
+      const int glen = m->fuse[oi];
+      const OpRecord* ex = glen == 3 ? &op : nullptr;
+      const OpRecord& dwop = m->ops[oi + glen - 2];
+      const OpRecord& pjop = m->ops[oi + glen - 1];
+      bool mb_taken = false;
+      if (int rc = launch_mbconv_umma(m, ex, dwop, pjop, tensor_ptr(op.in[0]), tensor_ptr(pjop.out), B, st, &mb_taken)) return rc;
+      if (mb_taken) covered = glen;
+    } else if (m->fuse[oi] > 1) {
       const int glen = m->fuse[oi];                        // 2: DW PW; 3: ADD DW PW; 4: ADD ADD DW PW
       const OpRecord* add0 = glen == 4 ? &op : nullptr;
       const OpRecord* add = glen >= 3 ? &m->ops[oi + glen - 3] : nullptr;

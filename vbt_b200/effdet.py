@@ -30,7 +30,7 @@ import numpy as np
 
 OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL, OP_LOGISTIC = 1, 2, 3, 4, 5, 6
 RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
-BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 10
+BLOB_MAGIC, BLOB_VERSION = 0x4d544256, 11
 
 VARIANTS = {
     # name: (input size, width, depth, fpn channels, fpn cells, head repeats)
@@ -476,6 +476,105 @@ def quantize(g: Graph, calib_frames):
     return g
 
 
+def mbconv_runs(g):
+    """{index of the first op: (expand op index or -1, depthwise index, project index)} for every
+    MBConv block the library runs as ONE kernel (csrc/mbconv_umma.cu): 1x1 expand (ReLU6) ->
+    depthwise 3x3 / 5x5, stride 1 / 2 (ReLU6) -> 1x1 project [+ the block input as residual], the
+    expanded tensor and the depthwise output living only in shared memory / TMEM.  The first block
+    of the backbone has no expand conv (expand ratio 1): depthwise -> project on a map too large
+    for the fused node kernel."""
+    n = len(g.ops)
+    readers = {}
+    for op in g.ops:
+        for t in op.inputs + ([op.residual] if op.residual >= 0 else []):
+            readers[t] = readers.get(t, 0) + 1
+    runs = {}
+
+    def dw_project(i, x):
+        if i + 1 >= n:
+            return False
+        d, p = g.ops[i], g.ops[i + 1]
+        return (d.type == OP_DW and d.k in (3, 5) and d.stride in (1, 2) and d.branch == 0 and
+                readers.get(d.out, 0) == 1 and p.type == OP_PW and p.inputs == [d.out] and p.out_kind == 0 and
+                p.branch == 0 and p.residual in (-1, x) and (p.residual < 0 or d.stride == 1) and
+                pad16(g.out_channels(p)) <= 352)
+
+    i = 0
+    while i < n:
+        e = g.ops[i]
+        if (e.type == OP_PW and e.out_kind == 0 and e.residual < 0 and e.branch == 0 and i + 2 < n and
+                readers.get(e.out, 0) == 1 and g.ops[i + 1].inputs == [e.out] and dw_project(i + 1, e.inputs[0]) and
+                g.tensors[e.inputs[0]].c_p <= 256):
+            runs[i] = (i, i + 1, i + 2)
+            i += 3
+        elif (e.type == OP_DW and g.tensors[e.out].c_p <= 32 and
+              max(g.tensors[e.inputs[0]].h, g.tensors[e.inputs[0]].w) > FUSE_MAX_HW and
+              dw_project(i, -2) and g.ops[i + 1].residual < 0):
+            runs[i] = (-1, i, i + 1)
+            i += 2
+        else:
+            i += 1
+    return runs
+
+
+def mbconv_image_layout(cin_p, k, cout_p, has_expand):
+    """Byte offsets inside one 32-expanded-channel chunk image (mirrored by csrc/mbconv_umma.cu):
+    (taps offset, project-weight offset, constants offset, image stride)."""
+    ge_in = (cin_p // 16 + 1) // 2 * 2
+    sz_wexp = 32 * ge_in * 16 if has_expand else 0
+    sz_taps = k * k * 32 * 4                      # pre-masked 32-bit weight words
+    off_taps = sz_wexp
+    off_wproj = off_taps + sz_taps
+    off_consts = off_wproj + cout_p * 32
+    stride = (off_consts + 512 + 127) // 128 * 128
+    return off_taps, off_wproj, off_consts, stride
+
+
+def mbconv_images(cin_p, k, cout_p, e, d, p):
+    """Per-chunk weight images of one MBConv block, each the exact shared-memory picture the fused
+    kernel wants (one bulk copy per chunk): the expand weights of 32 expanded channels as a K-major
+    no-swizzle core-matrix B operand, the 32 channels' depthwise taps [k*k][32] as pre-masked words, the project
+    weights' 32-wide K slice as a core-matrix B operand [cout_p][32], and the chunk's expand /
+    depthwise bias + multiplier vectors.  e / d / p: dict(w=int8 padded weights, bias=int32 folded,
+    mult=float32) of the three convs (e = None: no expand conv).
+    Core-matrix layout of a [N][K] operand: byte (n, kb) at ((n // 8) * (K // 16) + kb // 16) * 128 +
+    (n % 8) * 16 + kb % 16."""
+    off_taps, off_wproj, off_consts, stride = mbconv_image_layout(cin_p, k, cout_p, e is not None)
+    ge_in = (cin_p // 16 + 1) // 2 * 2
+    cexp = d['w'].shape[0]
+    n_chunks = (cexp + 31) // 32
+    out = np.zeros((n_chunks, stride), np.uint8)
+    nn = np.arange(32)
+    for c in range(n_chunks):
+        lo, hi = 32 * c, min(32 * c + 32, cexp)
+        m = hi - lo
+        if e is not None:
+            w = np.zeros((32, ge_in * 16), np.int8)
+            w[:m, :e['w'].shape[1]] = e['w'][lo:hi]
+            kb = np.arange(ge_in * 16)
+            off = ((nn[:, None] // 8) * ge_in + kb[None, :] // 16) * 128 + (nn[:, None] % 8) * 16 + kb[None, :] % 16
+            out[c, off.reshape(-1)] = w.view(np.uint8).reshape(-1)
+        # depthwise taps as pre-masked words: the weight of channel ch in byte ch % 4, zeros elsewhere, so
+        # dp4a(activation word of 4 channels, word) multiplies exactly one channel (no unpacking)
+        taps = np.zeros((k * k, 32), np.uint32)
+        tw = d['w'][lo:hi].reshape(m, k * k).T.astype(np.int64) & 0xff
+        taps[:, :m] = (tw << (8 * (np.arange(m) % 4))[None, :]).astype(np.uint32)
+        out[c, off_taps:off_taps + k * k * 128] = taps.view(np.uint8).reshape(-1)
+        wp = np.zeros((cout_p, 32), np.int8)
+        wp[:p['w'].shape[0], :m] = p['w'][:, lo:hi]
+        n2, k2 = np.arange(cout_p)[:, None], np.arange(32)[None, :]
+        off = ((n2 // 8) * 2 + k2 // 16) * 128 + (n2 % 8) * 16 + k2 % 16
+        out[c, off_wproj + off.reshape(-1)] = wp.view(np.uint8).reshape(-1)
+        consts = np.zeros(128, np.int32)
+        if e is not None:
+            consts[:m] = e['bias'][lo:hi]
+            consts[32:32 + m] = e['mult'][lo:hi].view(np.int32)
+        consts[64:64 + m] = d['bias'][lo:hi]
+        consts[96:96 + m] = d['mult'][lo:hi].view(np.int32)
+        out[c, off_consts:off_consts + 512] = consts.view(np.uint8)
+    return out, stride, n_chunks
+
+
 def fused_run_end(g):
     """run_end[i] = index of the last op of the [[ADD ->] ADD ->] DW3x3 s1 -> PW run op i may be executed
     in as one kernel (vbt_model_create's launch plan, csrc/model.cu), i itself otherwise.  A
@@ -501,9 +600,15 @@ def fused_run_end(g):
         return (o.type == OP_ADD and readers.get(o.out, 0) == 1 and dw_pw(i + 1) and
                 g.ops[i + 1].inputs == [o.out] and g.ops[i + 1].branch == o.branch)
 
+    for first, (_, _, last) in mbconv_runs(g).items():
+        for j in range(first, last + 1):
+            end[j] = last
     i = 0
     while i < n:
         o = g.ops[i]
+        if end[i] != i:
+            i = end[i] + 1
+            continue
         if (o.type == OP_ADD and len(o.inputs) == 2 and readers.get(o.out, 0) == 1 and i + 1 < n and
                 g.ops[i + 1].type == OP_ADD and len(g.ops[i + 1].inputs) == 2 and o.out in g.ops[i + 1].inputs and
                 g.ops[i + 1].branch == o.branch and add_dw_pw(i + 1)):
@@ -622,7 +727,7 @@ def _pack_op(rec):
                        f['out_elem_offset'])
     out += struct.pack('<3i i 3i 3i 3i ii 7i', *f['add_mult'], f['add_shift'], *f['resample'],
                        *f['in_h'], *f['in_w'], f['out_kind'], f['out_pix_stride'], f['branch'],
-                       f.get('requant_fast', 0), f.get('pw_dtype', 0), *([0] * 4))
+                       f.get('requant_fast', 0), f.get('pw_dtype', 0), *f.get('mb', [0, 0, 0, 0]))
     return out
 
 
@@ -654,8 +759,9 @@ def pack_blob(g: Graph):
     lut = np.exp(np.float32(g.box_scale) * (from_q - g.box_zp).astype(np.float32)).astype(np.float32)
     lut_off = put(lut)
     recs = []
+    conv = {}                  # op index -> padded weights / folded bias / multiplier (MBConv chunk images)
     a_per = NUM_SCALES * len(ASPECTS)
-    for op in g.ops:
+    for oi, op in enumerate(g.ops):
         q = op.q
         ins = [g.tensors[i] for i in op.inputs]
         tout = g.tensors[op.out] if op.out >= 0 else None
@@ -705,6 +811,7 @@ def pack_blob(g: Graph):
             mult = np.zeros(cout_p, np.float32)
             mult[:cout] = q['mult']
             r['w_off'], r['bias_off'], r['scale_off'] = put(wp), put(bias), put(mult)
+            conv[oi] = dict(w=wp if op.type == OP_PW else q['w'], bias=bias, mult=mult)
             # the kernels' packed requantisation carries rint(acc * M) in 16-bit lanes: allowed only
             # where no input can push |acc * M| past 2^15 - 256 (csrc/requant.cuh)
             wabs = np.abs(w).reshape(cout, -1).sum(axis=1)
@@ -735,7 +842,18 @@ def pack_blob(g: Graph):
         elif op.out_kind == 2:
             r['out_pix_stride'] = a_per * 4
             r['out_elem_offset'] = op.level_offset * 4
-        recs.append(_pack_op(r))
+        recs.append(r)
+    # MBConv blocks: per-chunk weight images for the fused kernel, announced on the depthwise op's
+    # record (mb = [image offset / 256 + 1, image stride, chunks, first op of the run relative to it])
+    for first, (ei, di, pi) in mbconv_runs(g).items():
+        d_op = g.ops[di]
+        cin_p = g.tensors[g.ops[first].inputs[0]].c_p
+        img, stride, n_chunks = mbconv_images(cin_p, d_op.k, recs[pi]['cout_p'], conv[ei] if ei >= 0 else None,
+                                              conv[di], conv[pi])
+        off = put(img)
+        assert off % 256 == 0
+        recs[di]['mb'] = [off // 256 + 1, stride, n_chunks, first - di]
+    recs = [_pack_op(r) for r in recs]
     tens = b''.join(struct.pack('<q4i', t.ws_offset, t.h, t.w, t.c, t.c_p) for t in g.tensors)
     header_bytes = 128
     table = header_bytes + OP_RECORD_BYTES * len(recs) + 24 * len(g.tensors)

@@ -89,6 +89,12 @@ class Detector:
         _lib.check(_lib.lib().vbt_model_plan(self.handle, _lib.ptr(g)))
         return g[:self.n_ops]
 
+    def plan_kinds(self):
+        """int32 [n_ops]: 1 where the launch starting at the op is a whole MBConv block."""
+        g = np.zeros(max(self.n_ops, 1), dtype=np.int32)
+        _lib.check(_lib.lib().vbt_model_plan_kinds(self.handle, _lib.ptr(g)))
+        return g[:self.n_ops]
+
     def op_times(self):
         """(ms per op accumulated [n_ops], number of vbt_detect calls covered)."""
         ms = np.zeros(max(self.n_ops, 1), dtype=np.float64)

@@ -71,7 +71,7 @@ class VideoPipeline:
     N_SLOTS = max(2, int(os.environ.get('VBT_SLOTS', '32')))
 
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
-                 row_cap=1 << 17, id_lanes=32, tracker_kw=None, diff_threshold=0.6,
+                 row_cap=1 << 17, id_lanes=64, tracker_kw=None, diff_threshold=0.6,
                  min_distance=0.1, n_lanes=None, keep_details=False):
         self.torch = t = _lib.require_cuda()
         if n_lanes is None:
@@ -320,6 +320,13 @@ class VideoPipeline:
         st.tracker.check_status()
         phases, count, state = st.lanes.read()
         rows = st.tracker.rows_host(0)
+        # every id the tracker emitted needs a velocity lane (lane l follows id l + 1); an id past the
+        # lanes would silently get no phases and no path length -- the reference's plot.py can
+        # analyse any id (plot.py:88), so this is a capacity error, not a truncation
+        if len(rows) and int(rows[:, 0].max()) > self.id_lanes:
+            raise _lib.VbtError(_lib.ECAPACITY,
+                                f'track id {int(rows[:, 0].max())} exceeds the {self.id_lanes} velocity lanes of '
+                                f'this VideoPipeline; construct it with id_lanes >= the number of tracks born')
         out_ph, out_path = {}, {}
         for l in range(self.id_lanes):
             if state[l, 2] > 0:
