@@ -5,11 +5,15 @@
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port), rank 0
 
 A *step* is one pass of the whole hot path (K1 preprocess -> EfficientDet-Lite0 int8 ->
-K6 post-process -> threshold/pack -> K7 tracker -> K8 velocity) over one batch of 64
-synthetic 1080p frames of a 1800-frame, 30 fps clip (BASELINE.json configs[1], frame
-stride 1).  `value` = frames/s with the clip already resident in HBM; `e2e` = the same
-with frames starting in pinned HOST memory (H2D inside the timed region, per-step result
-read back).  One JSON line on stdout (rank 0).
+K6 post-process -> threshold/pack -> K7 tracker -> K8 velocity -> end_processing -> rows and
+phases on the host) over ONE WHOLE synthetic 1080p clip of 1800 frames at 30 fps, fed in frame
+batches of 64 (BASELINE.json configs[1], frame stride 1): 29 batches plus the hand-over to the
+next clip.  `value` = frames/s with the clip already resident in HBM; `e2e` = the same with
+frames starting in pinned HOST memory (H2D inside the timed region, per-batch result read
+back).  One JSON line on stdout (rank 0).
+
+    python bench.py --workload configs4 --gpus N   # 34 clips with the dfs_ocsort fixture lengths,
+                                                   # sharded by whole videos (LPT), one NCCL gather
 """
 from __future__ import annotations
 
@@ -34,8 +38,8 @@ CLIP_FRAMES, FPS, BATCH = 1800, 30.0, 64
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=290)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=10, help='timed steps; a step is one whole clip')
+    ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--variant', default='lite0')
     ap.add_argument('--head-dtype', default='int8', choices=['int8', 'bf16'],
@@ -45,6 +49,9 @@ def parse():
     ap.add_argument('--cpu-sample', type=int, default=12, help='frames timed for cpu_baseline')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--videos', type=int, default=1,
+                    help='clips that advance together on one GPU, sharing the detection batches (K7: one warp each)')
+    ap.add_argument('--workload', default='configs1', choices=['configs1', 'configs4'])
     ap.add_argument('--op-dump', default=None, help='write per-op device times (tsv) to this path')
     ap.add_argument('--profiler-range', action='store_true',
                     help='cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)')
@@ -186,6 +193,94 @@ def run_reference(args, rank):
     }))
 
 
+# frame counts and frame rates of the 34 dfs_ocsort fixtures (BASELINE.json configs[4]: "34 synthetic 1080p
+# videos, one per dfs/ rep set"), 55,001 frames in total
+CONFIGS4_FRAMES = [2790, 1206, 1343, 2081, 2136, 1821, 936, 1617, 1692, 2102, 2155, 1975, 1965, 1986, 2329, 1736, 759,
+                   976, 1082, 1138, 1039, 2035, 915, 901, 1405, 1282, 1134, 1890, 849, 3243, 3133, 1119, 1270, 961]
+CONFIGS4_FPS = [60.0 if i in (0, 29, 30) else 30.0 for i in range(34)]
+
+
+class CycledFrames:
+    """A video of `n` frames that cycles through a shorter device-resident clip (34 distinct 1080p clips
+    would be 342 GB): indexable by a contiguous slice like the tensors shard.track_videos expects."""
+
+    def __init__(self, base, n, phase):
+        self.base, self.n, self.phase = base, int(n), int(phase)
+        self.shape = (self.n,) + tuple(base.shape[1:])
+        self.device = base.device
+
+    def __getitem__(self, sl):
+        import torch
+        L = self.base.shape[0]
+        a, b = (sl.start or 0) + self.phase, (sl.stop if sl.stop is not None else self.n) + self.phase
+        if a // L == (b - 1) // L:
+            return self.base[a % L:(b - 1) % L + 1]
+        return torch.cat([self.base[a % L:], self.base[:b % L]])      # the batch that wraps around
+
+
+def run_configs4(args, g, det, rank, world):
+    """BASELINE.json configs[4]: 34 clips with the fixture lengths, sharded by whole videos across the
+    ranks (greedy LPT on frame count), ONE NCCL gather of the track tables; checked on the GPUs against
+    a 1-rank run of the same videos (tables byte for byte)."""
+    import torch
+    import torch.distributed as dist
+    from vbt_b200 import _lib, shard
+    from vbt_b200.synth import plate_trajectory, render_clip
+    base = render_clip(args.clip_frames, H, W, seed=0, device='cuda', trajectory=plate_trajectory(args.clip_frames, FPS, seed=0))
+    videos = [{'fps': CONFIGS4_FPS[i], 'frames': CycledFrames(base, n, 53 * i)} for i, n in enumerate(CONFIGS4_FRAMES)]
+    counts = list(CONFIGS4_FRAMES)
+    plan = shard.lpt_assign(counts, world)
+    loads = [sum(counts[i] for i in p) for p in plan]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up = the whole workload once (graph capture per lane, NCCL channel set-up), then the timed pass
+    shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14)
+    barrier()
+    launches0 = _lib.lib().vbt_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    tables, _ = shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14)
+    ev1.record()
+    barrier()
+    launches = _lib.lib().vbt_launch_count() - launches0
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    parity, single = None, None
+    if rank == 0:                       # the same 34 videos on this GPU alone, no collective
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ref, _ = shard.track_videos(videos, det, 0.5, rank=0, world=1, gather=False, row_cap=1 << 14)
+        torch.cuda.synchronize()
+        single = sum(counts) / (time.perf_counter() - t0)
+        same = sum(1 for v in range(len(videos)) if np.array_equal(tables[v], ref[v]))
+        rows = int(sum(len(tables[v]) for v in range(len(videos))))
+        parity = {'videos_byte_identical_to_1_rank_run': same, 'videos': len(videos), 'rows': rows}
+        if same != len(videos):
+            raise SystemExit(f'configs4: only {same} of {len(videos)} gathered tables equal the 1-rank tables')
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        value = sum(counts) / (ms / 1e3)
+        emit(json.dumps({
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': 1, 'warmup': 1,
+            'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'int8',
+            'data': 'synthetic', 'gpu_launches': int(launches),
+            'config': {'workload': 'configs[4]: 34 synthetic 1080p clips with the dfs_ocsort fixture lengths (55,001 frames), '
+                                   'Lite0, frame batch 64, sharded by whole videos (greedy LPT), one NCCL gather of the track tables',
+                       'batch': args.batch, 'frames': sum(counts), 'rank_loads_frames': loads,
+                       'lpt_bound_efficiency': sum(counts) / world / max(loads),
+                       'single_rank_frames_per_s_same_job': single,
+                       'efficiency_vs_single_rank': (value / world / single) if single else None,
+                       'cache': 'inputs larger than L2: 398 MB of frames per batch'},
+            'parity': parity}))
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything libraries print meanwhile (NCCL's
     version banner, warnings) was redirected to stderr at start-up."""
@@ -219,38 +314,75 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     B = args.batch
+    V = args.videos
     g = effdet.build_synthetic(args.variant, head_dtype=args.head_dtype)
     det = Detector(g, max_batch=B)
-    pipe = VideoPipeline(det, FPS, 0.5, row_cap=1 << 17)
-    # every rank owns one whole video (weak scaling: videos are the shard unit)
-    clip = render_clip(args.clip_frames, H, W, seed=rank, device='cuda',
-                       trajectory=plate_trajectory(args.clip_frames, FPS, seed=rank))
-    n_batches = (args.clip_frames + B - 1) // B
-    numbers = torch.arange(1, args.clip_frames + 1, dtype=torch.int32, device='cuda')
-    state = {'cursor': 0, 'frames': 0, 'videos': 0, 'host_s': 0.0}
+    if args.workload == 'configs4':
+        run_configs4(args, g, det, rank, world)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    assert B % V == 0, 'the frame batch must hold equally many frames of every video'
+    pipe = VideoPipeline(det, FPS, 0.5, row_cap=1 << 17, n_videos=V)
+    # every rank owns its own clip(s) (weak scaling: whole videos are the shard unit).
+    # V > 1: V clips advance together, each batch holds B / V frames of every clip, video-major.
+    f = B // V
+    n_batches = (args.clip_frames + f - 1) // f
+    clips = [render_clip(args.clip_frames, H, W, seed=rank * V + v, device='cuda',
+                         trajectory=plate_trajectory(args.clip_frames, FPS, seed=rank * V + v)) for v in range(V)]
+    if V == 1:
+        clip = clips[0]
+    else:                                            # interleave once, outside every timed region
+        parts = []
+        for b in range(n_batches):
+            s, e = b * f, min((b + 1) * f, args.clip_frames)
+            parts.extend(c[s:e] for c in clips)
+        clip = torch.cat(parts)
+        del parts
+    del clips
+    numbers1 = torch.arange(1, args.clip_frames + 1, dtype=torch.int32, device='cuda')
+    frames_per_clip_step = args.clip_frames * V
+    state = {'frames': 0, 'videos': 0, 'host_s': 0.0, 'batches': 0, 'pending': None, 'last': None}
 
     def batch_range(b):
-        return b * B, min((b + 1) * B, args.clip_frames)
+        """(first, last) frame of batch b in `clip`, and the frame numbers of its frames."""
+        s, e = b * f, min((b + 1) * f, args.clip_frames)
+        return s * V, e * V, (numbers1[s:e] if V == 1 else numbers1[s:e].repeat(V))
 
-    def one_step(src=None):
-        b = state['cursor'] % n_batches
-        if b == 0 and state['cursor'] > 0:
-            # end of the clip: end_processing() + rows / phases to the host.  next_video() queues
-            # that behind the clip's last tracker step and lets the next clip's batches enter the
-            # device at once; the hand-over collects the clip before it (long finished) -- nothing
-            # drains between videos.  VBT_BENCH_DRAIN=1: the synchronous finish() + reset() instead.
-            if os.environ.get('VBT_BENCH_DRAIN') == '1':
-                state['last'] = pipe.finish()
-                pipe.reset()
-            else:
-                state['pending'] = pipe.next_video()
-            state['videos'] += 1
-        s, e = batch_range(b)
+    batch_numbers = [batch_range(b)[2].contiguous() for b in range(n_batches)]
+
+    def one_batch(b, src=None):
+        s, e, _ = batch_range(b)
         t0 = time.perf_counter()
-        pipe.process(clip[s:e] if src is None else src[:e - s], numbers[s:e], swap_rb=True)
+        pipe.process(clip[s:e] if src is None else src[:e - s], batch_numbers[b], swap_rb=True)
         state['host_s'] += time.perf_counter() - t0
-        state['cursor'] += 1
+        state['batches'] += 1
         state['frames'] += e - s
+
+    def end_of_clip():
+        """end_processing() + rows / phases to the host.  next_video() queues that behind the clip's last
+        tracker step and lets the next clip's batches enter the device at once; the clip before it
+        (long finished) is collected here -- nothing drains between videos.  VBT_BENCH_DRAIN=1: the
+        synchronous finish() + reset() instead."""
+        if os.environ.get('VBT_BENCH_DRAIN') == '1':
+            state['last'] = pipe.finish()
+            pipe.reset()
+        else:
+            if state['pending'] is not None:
+                state['last'] = state['pending'].result()
+            state['pending'] = pipe.next_video()
+        state['videos'] += V
+
+    def one_step():
+        """One whole clip (per video): every batch, then the hand-over."""
+        for b in range(n_batches):
+            one_batch(b)
+        end_of_clip()
+
+    def collect_tail():
+        if state['pending'] is not None:               # every finished clip reaches the host inside the timed region
+            state['last'] = state['pending'].result()
+            state['pending'] = None
 
     def barrier():
         if world > 1:
@@ -261,11 +393,14 @@ def main():
         """The one exchange step: counts, then padded row tables, over NCCL."""
         if world == 1:
             return
-        cnt = pipe.tracker.row_count.clone()
+        last = state['last'][0] if isinstance(state['last'], list) else state['last']
+        rows = torch.as_tensor(last['rows'] if last is not None else np.zeros((0, 8)), device='cuda').reshape(-1, 8)
+        cnt = torch.tensor([rows.shape[0]], dtype=torch.int64, device='cuda')
         counts = [torch.zeros_like(cnt) for _ in range(world)]
         dist.all_gather(counts, cnt)
-        mx = int(max(int(c.item()) for c in counts))
-        pad = pipe.tracker.rows[0, :max(mx, 1)].contiguous()
+        mx = max(int(max(int(c.item()) for c in counts)), 1)
+        pad = torch.zeros((mx, 8), dtype=torch.float64, device='cuda')
+        pad[:rows.shape[0]] = rows
         out = [torch.empty_like(pad) for _ in range(world)]
         dist.all_gather(out, pad)
 
@@ -273,16 +408,19 @@ def main():
         pipe._sync_streams()
 
     # ---- device-resident throughput (`value`) -------------------------------------------
-    for _ in range(max(args.warmup, 3)):          # >= 3: direct run, graph capture, first replay
+    for _ in range(max(args.warmup, 1)):          # a clip is 29 batches: direct run, graph capture, replays
         one_step()
+    collect_tail()
+    current_wait_all()
+    gather_tables()                               # first use sets up NCCL's all-gather channels: not in the timed region
     # one sampler per job (rank 0's GPU): eight nvidia-smi loops on one host steal the cores the
     # ranks enqueue from and serialise on the driver's NVML lock
     sampler = ClockSampler(local_rank if rank == 0 else None)
     barrier()
     sampler.start()
     launches0 = _lib.lib().vbt_launch_count()
-    frames0 = state['frames']
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    frames0, batches0 = state['frames'], state['batches']
+    ev0, ev1, ev2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     if args.profiler_range:
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
@@ -290,39 +428,43 @@ def main():
     state['host_s'] = 0.0
     for _ in range(args.steps):
         one_step()
-    host_ms = 1e3 * state['host_s'] / args.steps       # host time to ENQUEUE a step (process() only)
-    if state.get('pending') is not None:               # every finished clip reaches the host inside the timed region
-        state['last'] = state['pending'].result()
+    host_ms = 1e3 * state['host_s'] / max(state['batches'] - batches0, 1)   # host time to ENQUEUE one batch
+    collect_tail()
     current_wait_all()
-    gather_tables()
     ev1.record()
+    gather_tables()
+    ev2.record()
     if args.profiler_range:
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
     barrier()
     clocks = sampler.stop()
-    ms = ev0.elapsed_time(ev1)
+    ms = ev0.elapsed_time(ev2)
+    gather_ms = ev1.elapsed_time(ev2)
     frames = state['frames'] - frames0
     launches = _lib.lib().vbt_launch_count() - launches0
-    t = torch.tensor([ms], dtype=torch.float64, device='cuda')
+    t = torch.tensor([ms, gather_ms], dtype=torch.float64, device='cuda')
     ft = torch.tensor([float(frames)], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(ft, op=dist.ReduceOp.SUM)
-    ms_max, frames_all = float(t.item()), float(ft.item())
+    ms_max, gather_ms, frames_all = float(t[0].item()), float(t[1].item()), float(ft.item())
     value = frames_all / (ms_max / 1e3)
 
     # ---- per-kernel device times: the same steps again on ONE lane with an event after every
     #      op (vbt_model_profile) and around every stage, so kernels are timed alone --------------
     pipe.active_lanes = 1
-    one_step()
+    one_batch(0)
     det.profile(True)
     pipe.stage_events = []
     barrier()
     prof_frames0 = state['frames']
-    prof_steps = min(args.steps, 58)
-    for _ in range(prof_steps):
-        one_step()
+    prof_steps = min(2 * n_batches, 58)           # batches
+    for i in range(prof_steps):
+        one_batch((i + 1) % n_batches)
+        if (i + 2) % n_batches == 0:
+            end_of_clip()
+    collect_tail()
     current_wait_all()
     torch.cuda.synchronize()
     prof_frames = state['frames'] - prof_frames0
@@ -331,7 +473,7 @@ def main():
     stage_events, pipe.stage_events = pipe.stage_events, None
     pipe.active_lanes = len(pipe.detectors)
     # workload statistics of the last batch
-    dets_per_frame = float(pipe.det_count[pipe.last_slot, 0, :B].float().mean().item())
+    dets_per_frame = float(pipe.det_count[pipe.last_slot, 0, :f * V].float().mean().item())
     live_tracks = int(len(pipe.tracker.peek(0)))
 
     # ---- per-kernel breakdown + roofline of the dominant kernel ---------------------------
@@ -392,32 +534,47 @@ def main():
                 us = 1e3 * float(tms) / max(calls, 1)
                 f.write(f'{i}\t{name}\t{op.name}\t{t_in.h}x{t_in.w}\t{t_in.c}\t{g.out_channels(op)}\t{us:.2f}\t'
                         f'{by * B / (us * 1e3) if us > 0 else 0:.1f}\t{fl * B / (us * 1e6) if us > 0 else 0:.2f}\n')
-    k1_bytes = H * W * 3 + g.S * g.S * 3
+    # K1 reads only the source rows the bilinear resize touches (2 per output row, no antialias): charge
+    # those, not the whole frame (the ncu DRAM bytes agree: profiles/)
+    from vbt_b200.ingest import touched_rows
+    k1_bytes = len(touched_rows(H, g.S)) * W * 3 + g.S * g.S * 3
     kern['K1_preprocess'] = {'ms': stage_ms['K1_preprocess'], 'bytes_per_frame': k1_bytes,
                              'flops_per_frame': 0, 'launches_per_step': 1}
     for nme in ('K6_postprocess', 'pack', 'K7_tracker', 'K8_velocity'):
         kern[nme] = {'ms': stage_ms[nme], 'bytes_per_frame': 0, 'flops_per_frame': 0, 'launches_per_step': 1}
     total_kernel_ms = sum(k['ms'] for k in kern.values()) or 1.0
     hbm_peak, tf_peak, peak_src = measured_peaks()
-    # the dominant kernel of the detector's critical path (K7/K8 are latency-bound recurrences that
-    # run on the side stream, reported in `kernels` as us per frame)
+    # Roofline of the dominant kernel CLASS that has one (HBM-bound by arithmetic intensity); K7 / K8 are
+    # latency-bound recurrences (one warp per video): they enter the choice of `dominant_by_time` with
+    # bound "latency" and no roofline fraction.
+    bound_of = {n: ('latency' if kern[n]['bytes_per_frame'] == 0 else 'hbm') for n in kern}
+    by_time = max(kern, key=lambda n: kern[n]['ms'])
     dom_name = max((n for n in kern if kern[n]['bytes_per_frame'] > 0), key=lambda n: kern[n]['ms'])
     dom = kern[dom_name]
     dom_gbs = dom['bytes_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e9 if dom['ms'] > 0 else 0.0
     traffic = None
     try:
-        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
-            traffic = json.load(f).get(dom_name)
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as fh:
+            traffic = json.load(fh).get(dom_name)
     except Exception:
         pass
+    # end to end: frames/s against the binding ceiling of the whole path: one read of the
+    # source frame + the detection table (HBM) and the converter's op count on the tensor pipe
+    flops_per_frame = {'lite0': 1.752e9, 'lite1': 3.547e9, 'lite2': 6.066e9}[args.variant]
+    hbm_ceiling = hbm_peak * 1e9 / (H * W * 3 + 25 * 24 + 4)
+    tensor_ceiling = tf_peak * 1e12 / flops_per_frame
+    per_gpu = value / world
     roofline = {'kernel': dom_name, 'bound': 'hbm', 'achieved': dom_gbs, 'peak': hbm_peak,
                 'unit': 'GB/s', 'frac': dom_gbs / hbm_peak, 'traffic': traffic,
                 'peak_source': f'{peak_src} (MEASURED_PEAKS.json hbm_gbs)',
                 'share_of_step': dom['ms'] / total_kernel_ms,
                 'algorithmic_bytes_per_frame': dom['bytes_per_frame'],
                 'avg_launch_us': 1e3 * dom['ms'] / max(dom['launches_per_step'] * max(calls, 1), 1),
-                'tensor_tflops': dom['flops_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e12 if dom['ms'] > 0 else 0.0}
-    breakdown = {n: {'share': k['ms'] / total_kernel_ms,
+                'tensor_tflops': dom['flops_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e12 if dom['ms'] > 0 else 0.0,
+                'dominant_by_time': {'kernel': by_time, 'bound': bound_of[by_time], 'share_of_step': kern[by_time]['ms'] / total_kernel_ms},
+                'e2e_frac': per_gpu / min(hbm_ceiling, tensor_ceiling),
+                'e2e_ceilings_frames_per_s': {'hbm': hbm_ceiling, 'tensor_bf16_sustained': tensor_ceiling}}
+    breakdown = {n: {'share': k['ms'] / total_kernel_ms, 'bound': bound_of[n],
                      'gbs': (k['bytes_per_frame'] * frames_prof / (k['ms'] / 1e3) / 1e9) if k['ms'] > 0 and k['bytes_per_frame'] else None,
                      'ms_per_step': k['ms'] / max(prof_steps, 1)}
                  for n, k in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])}
@@ -428,40 +585,50 @@ def main():
         ring = 3
         host = [torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory() for _ in range(ring)]
         for i in range(ring):
-            s, e = batch_range(i % n_batches)
+            s, e, _ = batch_range(i % n_batches)
             host[i][:e - s].copy_(clip[s:e])
         res_host = torch.empty((B, det.max_det * 6 + 2), dtype=torch.float32).pin_memory()
         consumed = [None] * ring
-        main_stream = torch.cuda.current_stream()
         d2h_bytes = res_host.numel() * 4
 
         # Row-sparse ingest (vbt_b200/ingest.py): per batch, 16 strided DMA copies move only the
         # source rows the resize reads (2*S of the H rows) from pinned host memory.
         ing = pipe.use_row_sparse_ingest(H, W)
         h2d_bytes = B * ing.bytes_per_frame
+        e2e_i = {'i': 0}
 
-        def e2e_step(i):
+        def e2e_batch(b):
+            i = e2e_i['i']
+            e2e_i['i'] += 1
             slot = i % ring
             if consumed[slot] is not None:
                 consumed[slot].synchronize()       # a producer would refill this host buffer now
-            one_step(host[slot])
+            one_batch(b, host[slot])
             consumed[slot] = pipe.input_consumed
-            # the step's result: its packed detection table and the row count after K7/K8
+            # the batch's result: its packed detection table and the row count after K7/K8
             with torch.cuda.stream(pipe.side):
                 k = pipe.last_slot
                 res = torch.cat([pipe.dets[k, 0].reshape(B, -1).float(),
                                  pipe.det_count[k, 0, :, None].float(),
-                                 pipe.tracker.row_count.float().expand(B, 1)], dim=1)
+                                 pipe.tracker.row_count[:1].float().expand(B, 1)], dim=1)
                 res_host.copy_(res, non_blocking=True)
 
-        for i in range(args.warmup):
-            e2e_step(i)
+        def e2e_step():
+            for b in range(n_batches):
+                e2e_batch(b)
+            end_of_clip()
+
+        for _ in range(max(min(args.warmup, 2), 1)):
+            e2e_step()
+        collect_tail()
+        current_wait_all()
         barrier()
         f0 = state['frames']
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        for _ in range(args.steps):
+            e2e_step()
+        collect_tail()
         current_wait_all()
         gather_tables()
         b_.record()
@@ -472,15 +639,16 @@ def main():
             dist.all_reduce(ems, op=dist.ReduceOp.MAX)
             dist.all_reduce(efr, op=dist.ReduceOp.SUM)
         e2e = {'value': float(efr.item()) / (float(ems.item()) / 1e3), 'unit': 'frames/s',
-               'h2d_bytes_per_step': h2d_bytes, 'd2h_bytes_per_step': d2h_bytes,
-               'ms_per_step': float(ems.item()) / args.steps}
+               'h2d_bytes_per_step': h2d_bytes * n_batches, 'd2h_bytes_per_step': d2h_bytes * n_batches,
+               'ms_per_step': float(ems.item()) / args.steps,
+               'h2d_bytes_per_batch': h2d_bytes, 'd2h_bytes_per_batch': d2h_bytes}
 
     # ---- CPU baseline (rank 0, N=1 only) ----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle.cpu_pipeline import CpuPipeline
         n = args.cpu_sample
-        sample = clip[:n].cpu().numpy()
+        sample = clip[:n * V:V].cpu().numpy() if V > 1 else clip[:n].cpu().numpy()
         cp = CpuPipeline(g, FPS, 0.5)
         cp.step(sample[0], 1)
         cp.reset()
@@ -492,6 +660,19 @@ def main():
         cpu = {'value': n / dt, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
                'sample': f'first {n} frames of the same clip, one frame per invoke like track.py; '
                          f'int8-exact oracle chain (numpy + torch-CPU fp64 conv), not TFLite/XNNPACK'}
+        # a production int8 conv engine on the same graph (torch quantized: fbgemm / oneDNN), network only
+        try:
+            from oracle import effdet_q as OQ, resize as OR
+            qn = OQ.QuantNet(g)
+            imgs = [OR.resize_bilinear_u8(sample[i], g.S, swap_rb=True)[None] for i in range(min(n, 6))]
+            qn.run(imgs[0])
+            t0 = time.perf_counter()
+            for im in imgs:
+                qn.run(im)
+            cpu['network_only_int8_engine_frames_per_s'] = len(imgs) / (time.perf_counter() - t0)
+        except Exception as ex:       # the engine is optional equipment of the torch build
+            cpu['network_only_int8_engine_frames_per_s'] = None
+            cpu['int8_engine_error'] = str(ex)[:120]
         # the reference's own default is --threads 4 (track.py:72): the same port on four threads
         all_threads = torch.get_num_threads()
         if all_threads > 4 and n >= 4:
@@ -507,12 +688,14 @@ def main():
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'warmup': args.warmup, 'ms_per_step': ms_max / args.steps, 'ms_per_batch': ms_max / max(args.steps * n_batches, 1),
+            'gather_ms': gather_ms, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': 'int8', 'data': 'synthetic',
             'config': {
                 'workload': 'configs[1]: EfficientDet-Lite0 (synthetic int8 weights) full track.py '
                             'pipeline on one synthetic 1080p 30 fps 60 s clip per GPU, frame batch 64, '
-                            'frame stride 1',
+                            'frame stride 1; a step = one whole clip (29 batches + hand-over to the next clip)',
+                'step': f'{frames_per_clip_step} frames ({n_batches} batches of {B})', 'videos_per_gpu': V,
                 'variant': args.variant, 'head_dtype': args.head_dtype, 'batch': B, 'clip_frames': args.clip_frames,
                 'frames_per_timed_region': frames_all, 'videos_finished': state['videos'],
                 'detections_per_frame': dets_per_frame, 'live_tracks': live_tracks,

@@ -20,7 +20,26 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-from vbt_b200 import effdet as E     # graph description only (no compute is taken from it)
+# Nothing is imported from the product: the graph to interpret is passed in as data (ops with their
+# quantised weights), and the op codes / padding rules below are this file's own statement of them.
+# That the product's graph IS EfficientDet-Lite is checked separately against oracle/arch.py
+# (tests/test_oracle_arch.py); that the conv + requantisation arithmetic below agrees with an
+# unrelated production int8 engine is checked by oracle/effdet_q.py.
+OP_STEM, OP_PW, OP_DW, OP_ADD, OP_MAXPOOL = 1, 2, 3, 4, 5
+RS_NONE, RS_UP, RS_DOWN = 0, 1, 2
+ANCHORS_PER_LOCATION = 9            # 3 octaves x 3 aspect ratios
+
+
+def same_pad(size, k, stride):
+    """TF SAME: (output size, pad before)."""
+    out = -(-size // stride)
+    total = max((out - 1) * stride + k - size, 0)
+    return out, total // 2
+
+
+def nearest_index(dst, n_in, n_out):
+    """Legacy nearest-neighbour resize index (no half-pixel centres): floor(dst * in / out)."""
+    return (np.arange(dst) * n_in) // n_out
 
 
 FORCE_F64 = False      # tests flip this to check the float32 fast path against float64
@@ -35,8 +54,8 @@ def _requant(acc, mult, zp_out, lo, hi):
 
 
 def _same_pad(x, k, stride, value):
-    ho, pt = E.same_pad(x.shape[2], k, stride)
-    wo, pl = E.same_pad(x.shape[3], k, stride)
+    ho, pt = same_pad(x.shape[2], k, stride)
+    wo, pl = same_pad(x.shape[3], k, stride)
     pb = max((ho - 1) * stride + k - x.shape[2] - pt, 0)
     pr = max((wo - 1) * stride + k - x.shape[3] - pl, 0)
     return F.pad(x, (pl, pr, pt, pb), value=value)
@@ -54,7 +73,7 @@ def _add(xs, zps, mults, shift, zp_out, lo, hi):
     return y.clamp(lo, hi)
 
 
-def run(g: E.Graph, frames_u8, keep=False):
+def run(g, frames_u8, keep=False):
     """frames_u8: uint8 [B,S,S,3].  Returns (cls int8 [B,N], box int8 [B,N,4], tensors)
     where cls is the post-LOGISTIC score (scale 1/256, zp -128)."""
     B = frames_u8.shape[0]
@@ -62,12 +81,12 @@ def run(g: E.Graph, frames_u8, keep=False):
     N = g.n_anchors
     cls = np.zeros((B, N), np.int8)
     box = np.zeros((B, N, 4), np.int8)
-    a_per = E.NUM_SCALES * len(E.ASPECTS)
+    a_per = ANCHORS_PER_LOCATION
     with torch.no_grad():
         for op in g.ops:
             q = op.q
             ins = [vals[i] for i in op.inputs]
-            if op.type in (E.OP_STEM, E.OP_PW, E.OP_DW):
+            if op.type in (OP_STEM, OP_PW, OP_DW):
                 # float32 convolutions are exact while every partial sum stays below 2^24
                 # (|x - zp| <= 255, |w| <= 127): true for every layer with fan-in <= 518;
                 # wider ones (the 672 / 1152-channel projections) use float64
@@ -76,32 +95,32 @@ def run(g: E.Graph, frames_u8, keep=False):
                     else (torch.float64, np.float64)
                 x = (ins[0] - q['zp_in'][0]).to(ft)
                 w = torch.from_numpy(q['w'].astype(nt))
-                if op.type == E.OP_STEM:
+                if op.type == OP_STEM:
                     acc = F.conv2d(_same_pad(x, 3, 2, 0.0), w.permute(0, 3, 1, 2).contiguous(),
                                    stride=2)
-                elif op.type == E.OP_PW:
+                elif op.type == OP_PW:
                     acc = F.conv2d(x, w[:, :, None, None])
                 else:
                     acc = F.conv2d(_same_pad(x, op.k, op.stride, 0.0), w[:, None],
                                    stride=op.stride, groups=w.shape[0])
                 acc = acc.round().long() + torch.from_numpy(q['bias'].astype(np.int64))[None, :, None, None]
-                if op.type == E.OP_PW and op.residual >= 0:
+                if op.type == OP_PW and op.residual >= 0:
                     y = _requant(acc, q['mult'], q['conv_zp_out'], -128, 127)
                     y = _add([y, vals[op.residual]], [q['conv_zp_out'], q['res_zp']],
                              q['add_mult'], q['add_shift'], q['zp_out'], q['act_lo'], q['act_hi'])
                 else:
                     y = _requant(acc, q['mult'], q['conv_zp_out'], q['act_lo'], q['act_hi'])
-            elif op.type == E.OP_MAXPOOL:
+            elif op.type == OP_MAXPOOL:
                 y = _maxpool(ins[0])
-            elif op.type == E.OP_ADD:
+            elif op.type == OP_ADD:
                 t = g.tensors[op.out]
                 xs = []
                 for xin, rs in zip(ins, op.resample):
-                    if rs == E.RS_UP:
-                        iy = torch.from_numpy(E.nearest_index(t.h, xin.shape[2], t.h))
-                        ix = torch.from_numpy(E.nearest_index(t.w, xin.shape[3], t.w))
+                    if rs == RS_UP:
+                        iy = torch.from_numpy(nearest_index(t.h, xin.shape[2], t.h))
+                        ix = torch.from_numpy(nearest_index(t.w, xin.shape[3], t.w))
                         xin = xin[:, :, iy][:, :, :, ix]
-                    elif rs == E.RS_DOWN:
+                    elif rs == RS_DOWN:
                         xin = _maxpool(xin)
                     xs.append(xin)
                 y = _add(xs, q['zp_in'], q['add_mult'], q['add_shift'], q['zp_out'],

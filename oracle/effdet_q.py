@@ -156,3 +156,94 @@ def check_convs(g, frames_u8, exact_tensors):
             d = (y - want).abs()
             out.append((op.name, int(d.numel()), int((d > 0).sum()), int(d.max())))
     return out
+
+
+class QuantNet:
+    """The layer program with prepacked weights on the quantized engine: what `run` computes, arranged
+    for speed (weights packed once, activations kept as uint8 NCHW tensors between convolutions).
+    bench.py's CPU arm times this as the host-core baseline: a production int8 conv engine (fbgemm /
+    oneDNN, all host threads), the closest thing to the reference's TFLite/XNNPACK path that can run
+    here.  Results follow the exact oracle to within the engine's one-step rounding differences; it is
+    a speed baseline, never the parity arbiter."""
+
+    def __init__(self, g):
+        self.g = g
+        self.packed = {}
+        for i, op in enumerate(g.ops):
+            if op.type not in (OP_STEM, OP_PW, OP_DW):
+                continue
+            q = op.q
+            w = np.asarray(q['w'])
+            mult = np.asarray(q['mult'], np.float32)
+            if op.type == OP_STEM:
+                wt, k, stride, groups = torch.from_numpy(np.ascontiguousarray(w.transpose(0, 3, 1, 2))), 3, 2, 1
+            elif op.type == OP_PW:
+                wt, k, stride, groups = torch.from_numpy(np.ascontiguousarray(w[:, :, None, None])), 1, 1, 1
+            else:
+                wt, k, stride, groups = torch.from_numpy(np.ascontiguousarray(w[:, None])), op.k, op.stride, w.shape[0]
+            wq = torch._make_per_channel_quantized_tensor(wt.to(torch.int8), torch.from_numpy(mult.astype(np.float64)),
+                                                          torch.zeros(len(mult), dtype=torch.int64), 0)
+            bias = torch.from_numpy(np.asarray(q['bias'], np.float64) * mult.astype(np.float64)).float()
+            pk = torch.ops.quantized.conv2d_prepack(wq, bias, [stride, stride], [0, 0], [1, 1], groups)
+            self.packed[i] = (pk, k, stride)
+
+    def _conv(self, i, op, xu, lo, hi):
+        """xu: uint8 [B,C,H,W] (our int8 value + 128; the stem input as is).  Returns uint8."""
+        pk, k, stride = self.packed[i]
+        q = op.q
+        zp_u = int(q['zp_in'][0]) + (0 if op.type == OP_STEM else 128)
+        if k > 1:
+            pt, pb = _same_pad(xu.shape[2], k, stride)
+            pl, pr = _same_pad(xu.shape[3], k, stride)
+            xu = F.pad(xu, (pl, pr, pt, pb), value=zp_u)
+        xq = torch._make_per_tensor_quantized_tensor(xu.contiguous(memory_format=torch.channels_last), 1.0, zp_u)
+        y = torch.ops.quantized.conv2d(xq, pk, 1.0, int(q['conv_zp_out']) + 128).int_repr()
+        if lo > -128 or hi < 127:
+            y = y.clamp(lo + 128, hi + 128)
+        return y
+
+    def run(self, frames_u8):
+        g = self.g
+        B = frames_u8.shape[0]
+        vals = {g.input: torch.from_numpy(np.ascontiguousarray(frames_u8)).permute(0, 3, 1, 2)}
+        N = g.n_anchors
+        cls, box = np.zeros((B, N), np.int8), np.zeros((B, N, 4), np.int8)
+        with torch.no_grad():
+            for i, op in enumerate(g.ops):
+                q = op.q
+                ins = [vals[t] for t in op.inputs]
+                if op.type in (OP_STEM, OP_PW, OP_DW):
+                    if op.type == OP_PW and op.residual >= 0:
+                        y = self._conv(i, op, ins[0], -128, 127).long() - 128
+                        r = vals[op.residual].long() - 128
+                        y = (_add([y, r], [q['conv_zp_out'], q['res_zp']], q['add_mult'], q['add_shift'], q['zp_out'],
+                                  q['act_lo'], q['act_hi']) + 128).to(torch.uint8)
+                    else:
+                        y = self._conv(i, op, ins[0], q['act_lo'], q['act_hi'])
+                elif op.type == OP_MAXPOOL:
+                    y = (_maxpool(ins[0].long()) ).to(torch.uint8)
+                elif op.type == OP_ADD:
+                    t = g.tensors[op.out]
+                    xs = []
+                    for xin, rs in zip(ins, op.resample):
+                        xin = xin.long() - 128
+                        if rs == RS_UP:
+                            iy = (torch.arange(t.h) * xin.shape[2]) // t.h
+                            ix = (torch.arange(t.w) * xin.shape[3]) // t.w
+                            xin = xin[:, :, iy][:, :, :, ix]
+                        elif rs == RS_DOWN:
+                            xin = _maxpool(xin)
+                        xs.append(xin)
+                    y = (_add(xs, q['zp_in'], q['add_mult'], q['add_shift'], q['zp_out'], q['act_lo'], q['act_hi']) + 128).to(torch.uint8)
+                else:
+                    raise ValueError(op.type)
+                if op.out >= 0:
+                    vals[op.out] = y
+                else:
+                    yv = (y.long() - 128).permute(0, 2, 3, 1).numpy()
+                    n = yv.shape[1] * yv.shape[2] * 9
+                    if op.out_kind == 1:
+                        cls[:, op.level_offset:op.level_offset + n] = q['lut'][(yv.reshape(B, n) + 128).astype(np.int64)]
+                    else:
+                        box[:, op.level_offset:op.level_offset + n] = yv.reshape(B, n, 4).astype(np.int8)
+        return cls, box

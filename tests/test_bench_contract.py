@@ -50,3 +50,19 @@ def test_our_arm_line():
     c = d['cpu_baseline']
     assert c['value'] > 0 and c['cores'] >= 1 and c['kind'] == 'port' and c['sample']
     assert 'sm_mhz' in d['clocks'] and 'reasons' in d['clocks']
+    # a step is one whole clip; the NCCL gather is timed apart; the end-to-end roofline fraction and the
+    # kernel with the largest time share (K7 is allowed, bound "latency") are reported
+    assert d['config']['step'].startswith('192 frames') and d['gather_ms'] >= 0 and d['ms_per_batch'] > 0
+    assert 0 < r['e2e_frac'] < 1 and r['dominant_by_time']['bound'] in ('hbm', 'latency')
+    assert {'K7_tracker', 'K1_preprocess'} <= set(d['kernels']) and d['kernels']['K7_tracker']['bound'] == 'latency'
+    assert any(k == 'mbconv_fused' for k in d['kernels']), 'the backbone runs as fused MBConv blocks'
+
+
+@pytest.mark.gpu
+def test_configs4_workload_line():
+    """34 fixture-length clips through shard.track_videos (one rank here): every gathered table equals the
+    1-rank table; the line carries the LPT bound the sharding is measured against."""
+    d = run(['--workload', 'configs4', '--clip-frames', '256'])
+    assert d['config']['frames'] == 55001 and len(d['config']['rank_loads_frames']) == 1
+    assert d['parity']['videos_byte_identical_to_1_rank_run'] == d['parity']['videos'] == 34
+    assert d['parity']['rows'] > 0 and d['value'] > 1000 and d['scaling'] == 'strong'

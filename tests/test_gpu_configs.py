@@ -349,3 +349,115 @@ def test_next_video_overlaps_and_equals_finish_reset():
             assert [(p.time_start, p.time_end, p.rom, p.type) for p in w['phases'][tid]] == \
                    [(p.time_start, p.time_end, p.rom, p.type) for p in r['phases'][tid]]
     assert np.array_equal(oracle_rows(g, clips[2][1], 30.0, thr), got[2]['rows'])
+
+
+# ---- many videos per GPU, lane capacity, the bench configuration -----------------------------------
+
+def _phase_tuples(phases):
+    return {tid: [(p.time_start, p.time_end, p.y_start, p.y_end, p.rom, p.type) for p in ps] for tid, ps in phases.items()}
+
+
+@pytest.mark.parametrize('V', [2, 4])
+def test_videos_sharing_batches_equal_videos_alone(V):
+    """V videos whose frames travel in the same detection batches (K7: one warp per video, K8: one lane
+    per (video, id)) give exactly what each video gives alone -- and what the CPU oracle gives.  The
+    unit of independence is the video (track.py:88-101,157)."""
+    import torch
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    g = graph('lite0')
+    F, f, n, thr, fps = 8, 8 // V, 24, 0.3, 30.0
+    det = Detector(g, max_batch=F)
+    clips = [synthetic_frames(n, 135, 240, seed=40 + v) for v in range(V)]
+    alone = []
+    for v in range(V):
+        pipe = VideoPipeline(det, fps, thr, row_cap=4096)
+        for s in range(0, n, F):
+            pipe.process(torch.as_tensor(clips[v][s:s + F], device='cuda'),
+                         torch.arange(s + 1, min(s + F, n) + 1, dtype=torch.int32, device='cuda'), swap_rb=True)
+        alone.append(pipe.finish())
+        assert np.array_equal(alone[v]['rows'], oracle_rows(g, clips[v], fps, thr))
+    assert any(len(a['rows']) for a in alone)
+    pipe = VideoPipeline(det, fps, thr, row_cap=4096, n_videos=V)
+    for s in range(0, n, f):                               # video-major batches: f frames of each video
+        batch = np.concatenate([clips[v][s:s + f] for v in range(V)])
+        numbers = np.concatenate([np.arange(s + 1, s + f + 1) for _ in range(V)]).astype(np.int32)
+        pipe.process(torch.as_tensor(batch, device='cuda'), torch.as_tensor(numbers, device='cuda'), swap_rb=True)
+    handle = pipe.next_video()
+    together = handle.result()
+    assert len(together) == V
+    for v in range(V):
+        assert np.array_equal(together[v]['rows'], alone[v]['rows']), v
+        assert _phase_tuples(together[v]['phases']) == _phase_tuples(alone[v]['phases'])
+        assert together[v]['path'] == alone[v]['path']
+
+
+def test_more_tracks_than_velocity_lanes_is_a_capacity_error():
+    """A track id beyond `id_lanes` would get no phases: VBT_ECAPACITY instead of a silent loss."""
+    import torch
+    from vbt_b200 import _lib
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    g = graph('lite0')
+    det = Detector(g, max_batch=8)
+    pipe = VideoPipeline(det, 30.0, 0.3, row_cap=4096, id_lanes=2)
+    D = det.max_det
+    dets = torch.zeros((6, D, 6), dtype=torch.float64, device='cuda')
+    for i, (x, y) in enumerate([(0.1, 0.1), (0.5, 0.5), (0.8, 0.2)]):          # three well separated plates
+        dets[:, i] = torch.tensor([x, y, x + 0.1, y + 0.1, 0.9, 0.0], dtype=torch.float64)
+    counts = torch.full((6,), 3, dtype=torch.int32, device='cuda')
+    numbers = torch.arange(1, 7, dtype=torch.int32, device='cuda')
+    pipe.track_table(dets, counts, numbers)
+    with pytest.raises(_lib.VbtError) as e:
+        pipe.finish()
+    assert e.value.code == _lib.ECAPACITY
+    ok = VideoPipeline(det, 30.0, 0.3, row_cap=4096, id_lanes=3)
+    ok.track_table(dets, counts, numbers)
+    assert sorted(ok.finish()['phases']) == [1, 2, 3]
+
+
+def test_bench_configuration_matches_the_oracle():
+    """The BENCH line's exact path: Lite0, 1080p, frame batch 64, two detection lanes, CUDA-graph replay,
+    device-resident frames AND row-sparse ingest from pinned host memory -- rows and phases of three
+    batches (two replays of each lane's graph) against the CPU oracle chain (~20 s of CPU)."""
+    import torch
+    from vbt_b200.interpreter import Detector
+    from vbt_b200.pipeline import VideoPipeline
+    from vbt_b200.synth import plate_trajectory, render_clip
+    g = graph('lite0')
+    B, n, fps, thr = 64, 160, 30.0, 0.5
+    det = Detector(g, max_batch=B)
+    clip = render_clip(n, 1080, 1920, seed=0, device='cuda', trajectory=plate_trajectory(1800, fps, seed=0)[:n])
+    numbers = torch.arange(1, n + 1, dtype=torch.int32, device='cuda')
+    results = []
+    for mode in ('device', 'host'):
+        pipe = VideoPipeline(det, fps, thr, row_cap=1 << 14, n_lanes=2)
+        assert len(pipe.detectors) == 2
+        if mode == 'host':
+            assert pipe.use_row_sparse_ingest(1080, 1920) is not None
+            host = [torch.empty((B, 1080, 1920, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+        for rep in range(2):                              # second pass replays every lane's captured graph
+            for i, s in enumerate(range(0, n, B)):
+                e = min(s + B, n)
+                if mode == 'device':
+                    src = clip[s:e]
+                else:
+                    if pipe.input_consumed is not None:
+                        pipe.input_consumed.synchronize()
+                    host[i % 2][:e - s].copy_(clip[s:e])
+                    src = host[i % 2][:e - s]
+                pipe.process(src, numbers[s:e], swap_rb=True)
+            res = pipe.next_video().result() if rep == 0 else pipe.finish()
+            results.append(res)
+    frames_np = clip.cpu().numpy()
+    want = oracle_rows(g, frames_np, fps, thr)
+    assert len(want) >= n // 2                              # the plate (and some spurious boxes) are tracked
+    rows_by_id = {}
+    for tid in np.unique(want[:, 0]).astype(int):
+        rows_by_id[int(tid)] = ov.analyze_series(want[want[:, 0] == tid][:, 1:], 0.45)
+    for res in results:
+        assert np.array_equal(res['rows'], want)
+        assert sorted(res['phases']) == sorted(rows_by_id)
+        for tid, ps in res['phases'].items():
+            got = np.array([[p.time_start, p.time_end, p.y_start, p.y_end, p.rom, p.type] for p in ps]).reshape(-1, 6)
+            assert np.array_equal(got, rows_by_id[tid])

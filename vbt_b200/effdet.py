@@ -522,7 +522,7 @@ def mbconv_image_layout(cin_p, k, cout_p, has_expand):
     (taps offset, project-weight offset, constants offset, image stride)."""
     ge_in = (cin_p // 16 + 1) // 2 * 2
     sz_wexp = 32 * ge_in * 16 if has_expand else 0
-    sz_taps = k * k * 32 * 4                      # pre-masked 32-bit weight words
+    sz_taps = k * (2 if k == 5 else 1) * 32 * 4   # [k rows][1 or 2 words][32 channels] u32
     off_taps = sz_wexp
     off_wproj = off_taps + sz_taps
     off_consts = off_wproj + cout_p * 32
@@ -533,7 +533,7 @@ def mbconv_image_layout(cin_p, k, cout_p, has_expand):
 def mbconv_images(cin_p, k, cout_p, e, d, p):
     """Per-chunk weight images of one MBConv block, each the exact shared-memory picture the fused
     kernel wants (one bulk copy per chunk): the expand weights of 32 expanded channels as a K-major
-    no-swizzle core-matrix B operand, the 32 channels' depthwise taps [k*k][32] as pre-masked words, the project
+    no-swizzle core-matrix B operand, the 32 channels' depthwise taps packed four horizontal taps to a word [k][1 or 2][32], the project
     weights' 32-wide K slice as a core-matrix B operand [cout_p][32], and the chunk's expand /
     depthwise bias + multiplier vectors.  e / d / p: dict(w=int8 padded weights, bias=int32 folded,
     mult=float32) of the three convs (e = None: no expand conv).
@@ -554,12 +554,14 @@ def mbconv_images(cin_p, k, cout_p, e, d, p):
             kb = np.arange(ge_in * 16)
             off = ((nn[:, None] // 8) * ge_in + kb[None, :] // 16) * 128 + (nn[:, None] % 8) * 16 + kb[None, :] % 16
             out[c, off.reshape(-1)] = w.view(np.uint8).reshape(-1)
-        # depthwise taps as pre-masked words: the weight of channel ch in byte ch % 4, zeros elsewhere, so
-        # dp4a(activation word of 4 channels, word) multiplies exactly one channel (no unpacking)
-        taps = np.zeros((k * k, 32), np.uint32)
-        tw = d['w'][lo:hi].reshape(m, k * k).T.astype(np.int64) & 0xff
-        taps[:, :m] = (tw << (8 * (np.arange(m) % 4))[None, :]).astype(np.uint32)
-        out[c, off_taps:off_taps + k * k * 128] = taps.view(np.uint8).reshape(-1)
+        # depthwise taps for the planar dp4a form: per window row ky, word 0 = taps kx 0..3 of the channel
+        # in its four bytes (kx 3 = 0 for 3x3), word 1 (5x5 only) = tap kx 4 in byte 0
+        nww = 2 if k == 5 else 1
+        tw = np.zeros((k, nww * 4, 32), np.int64)
+        tw[:, :k, :m] = (d['w'][lo:hi].astype(np.int64) & 0xff).transpose(1, 2, 0)       # [ky][kx][ch]
+        words = tw.reshape(k, nww, 4, 32)
+        taps = (words[:, :, 0] | (words[:, :, 1] << 8) | (words[:, :, 2] << 16) | (words[:, :, 3] << 24)).astype(np.uint32)
+        out[c, off_taps:off_taps + k * nww * 128] = taps.view(np.uint8).reshape(-1)
         wp = np.zeros((cout_p, 32), np.int8)
         wp[:p['w'].shape[0], :m] = p['w'][:, lo:hi]
         n2, k2 = np.arange(cout_p)[:, None], np.arange(32)[None, :]

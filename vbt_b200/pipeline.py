@@ -22,20 +22,23 @@ COLUMNS = ['id', 'time', 'x', 'y', 'dx', 'dy', 'norm_plate_height', 'norm_plate_
 
 
 class _VideoState:
-    """Tracker + velocity state of ONE video.  The pipeline owns two and alternates, so the next
-    video's batches enter the device while the previous video's tail (last tracker steps,
-    end_processing, read-back) is still in flight -- `VideoPipeline.next_video`."""
+    """Tracker + velocity state of ONE video -- or of `n_videos` videos that advance in lock step
+    (their frames share the detection batches; K7 runs one warp per video, K8 one lane per (video,
+    id)).  The pipeline owns two sets and alternates, so the next video's batches enter the device
+    while the previous video's tail (last tracker steps, end_processing, read-back) is still in
+    flight -- `VideoPipeline.next_video`."""
 
-    def __init__(self, t, row_cap, id_lanes, keep_details, tracker_kw, fps=30.0):
+    def __init__(self, t, row_cap, id_lanes, keep_details, tracker_kw, fps=30.0, n_videos=1):
         # the tracker recurrence is one warp per video and nearly as long as a detection step: each
         # video gets its own (high-priority) stream, so the tail of one video's recurrence runs
         # beside the head of the next one's instead of in front of it
         self.side = t.cuda.Stream(priority=-1)
-        self.d_fps = t.tensor([float(fps)], dtype=t.float64, device='cuda')
-        self.tracker = BatchedTracker(1, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
-        self.lanes = _Lanes(id_lanes, path_cap=min(row_cap, 1 << 15))
-        self.lane_table = t.zeros(id_lanes, dtype=t.int32, device='cuda')
-        self.lane_begin = t.zeros(id_lanes, dtype=t.int32, device='cuda')
+        self.d_fps = t.full((n_videos,), float(fps), dtype=t.float64, device='cuda')
+        self.tracker = BatchedTracker(n_videos, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
+        self.lanes = _Lanes(n_videos * id_lanes, path_cap=min(row_cap, 1 << 15))
+        # lane v * id_lanes + l follows id l + 1 of video v (row table v)
+        self.lane_table = t.arange(n_videos, dtype=t.int32, device='cuda').repeat_interleave(id_lanes).contiguous()
+        self.lane_begin = t.zeros(n_videos * id_lanes, dtype=t.int32, device='cuda')
         self.frame_log = []             # (frame numbers, detection counts) per batch, for the overlay export
         self.pending = None             # _PendingVideo not collected yet
 
@@ -72,7 +75,12 @@ class VideoPipeline:
 
     def __init__(self, detector: Detector, fps, detection_threshold=0.5, plate_diameter=0.45,
                  row_cap=1 << 17, id_lanes=64, tracker_kw=None, diff_threshold=0.6,
-                 min_distance=0.1, n_lanes=None, keep_details=False):
+                 min_distance=0.1, n_lanes=None, keep_details=False, n_videos=1):
+        """n_videos = V > 1: V videos advance together.  Every batch handed to `process` holds the
+        same number of frames of each, video-major ([v0 f0..fk, v1 f0..fk, ...]); `finish()` /
+        `next_video().result()` return a list of V result dicts.  The videos are independent
+        (track.py:88-101,157: fresh tracker per video) -- sharing batches changes no result, it
+        turns K7's one-warp recurrence into V warps of a V-times shorter one."""
         self.torch = t = _lib.require_cuda()
         if n_lanes is None:
             n_lanes = max(1, int(os.environ.get('VBT_LANES', '2')))
@@ -83,7 +91,10 @@ class VideoPipeline:
         self.F = detector.max_batch
         self.keep_details = keep_details
         self.id_lanes = id_lanes
-        self._state_args = (t, row_cap, id_lanes, keep_details, tracker_kw, self.fps)
+        self.V = int(n_videos)
+        if self.V < 1 or detector.max_batch % self.V:
+            raise ValueError(f'n_videos={n_videos} must divide the detector batch {detector.max_batch}')
+        self._state_args = (t, row_cap, id_lanes, keep_details, tracker_kw, self.fps, self.V)
         self.states = [_VideoState(*self._state_args), _VideoState(*self._state_args)]
         self.cur = 0
         D = detector.max_det
@@ -91,8 +102,9 @@ class VideoPipeline:
         self.dets = t.zeros((S, 1, self.F, D, 6), dtype=t.float64, device='cuda')
         self.det_count = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
         self.frame_no = t.zeros((S, 1, self.F), dtype=t.int32, device='cuda')
-        self.n_frames = t.zeros((S, 1), dtype=t.int32, device='cuda')
-        self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda')
+        self.n_frames = t.zeros((S, self.V), dtype=t.int32, device='cuda')
+        self.lane_id = t.arange(1, id_lanes + 1, dtype=t.int32, device='cuda').repeat(self.V).contiguous()
+        self.n_velocity_lanes = self.V * id_lanes
         self.detectors = [detector] + [Detector(detector.source, max_batch=detector.max_batch,
                                                 iou_threshold=detector.iou_threshold,
                                                 max_det=detector.max_det) for _ in range(n_lanes - 1)]
@@ -204,7 +216,9 @@ class VideoPipeline:
                 self.threshold, self.dets[k].data_ptr(), self.det_count[k].data_ptr(),
                 _lib.stream_ptr(ds)))
             self.frame_no[k, 0, :n].copy_(frame_numbers, non_blocking=True)
-            self.n_frames[k].fill_(n)
+            if n % self.V:
+                raise ValueError(f'a batch of {n} frames cannot hold equally many of {self.V} videos')
+            self.n_frames[k].fill_(n // self.V)
             if self.keep_details:
                 self._frame_log.append((self.frame_no[k, 0, :n].clone(), self.det_count[k, 0, :n].clone()))
             self._mark(marks)
@@ -221,11 +235,13 @@ class VideoPipeline:
         side.wait_event(self.det_ready[k])             # batches reach the side stream in order
         with t.cuda.stream(side):
             self._mark(marks, side)
-            self.tracker.update(self.dets[k], self.det_count[k], self.frame_no[k], self.d_fps,
-                                self.n_frames[k], stream=side)
+            # video-major batch: the first n frame slots viewed as [V, n / V, ...] are each video's own
+            f = n // self.V
+            self.tracker.update(self.dets[k, 0, :n].view(self.V, f, -1, 6), self.det_count[k, 0, :n].view(self.V, f),
+                                self.frame_no[k, 0, :n].view(self.V, f), self.d_fps, self.n_frames[k], stream=side)
             self._mark(marks, side)
             self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
-                              self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
+                              self.lane_table, self.lane_id, self.lane_begin, self.n_velocity_lanes,
                               self.plate_diameter, self.diff_threshold, self.min_distance,
                               smooth=True, finish=False)
             self._mark(marks, side)
@@ -250,6 +266,7 @@ class VideoPipeline:
         """K7 + K8 over a detection table (the output of `detection_table`, possibly gathered from
         several ranks), in frame order, `max_batch` frames per tracker call."""
         t = self.torch
+        assert self.V == 1, 'track_table replays ONE video\'s detection table'
         self._sync_streams()
         side = self.side
         side.wait_stream(t.cuda.current_stream())
@@ -266,7 +283,7 @@ class VideoPipeline:
                 self.tracker.update(self.dets[k], self.det_count[k], self.frame_no[k], self.d_fps,
                                     self.n_frames[k], stream=side)
                 self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
-                                  self.lane_table, self.lane_id, self.lane_begin, self.id_lanes,
+                                  self.lane_table, self.lane_id, self.lane_begin, self.n_velocity_lanes,
                                   self.plate_diameter, self.diff_threshold, self.min_distance,
                                   smooth=True, finish=False)
                 self.slot_free[k].record(side)
@@ -280,7 +297,7 @@ class VideoPipeline:
         self._sync_streams()
         st = self.states[self.cur]
         st.lanes.update(st.tracker.rows, st.tracker.row_count, st.tracker.row_cap,
-                        st.lane_table, self.lane_id, st.lane_begin, self.id_lanes,
+                        st.lane_table, self.lane_id, st.lane_begin, self.n_velocity_lanes,
                         self.plate_diameter, self.diff_threshold, self.min_distance,
                         smooth=True, finish=True)
         return self._collect(st)
@@ -294,7 +311,7 @@ class VideoPipeline:
         st = self.states[self.cur]
         with t.cuda.stream(st.side):
             st.lanes.update(st.tracker.rows, st.tracker.row_count, st.tracker.row_cap,
-                            st.lane_table, self.lane_id, st.lane_begin, self.id_lanes,
+                            st.lane_table, self.lane_id, st.lane_begin, self.n_velocity_lanes,
                             self.plate_diameter, self.diff_threshold, self.min_distance,
                             smooth=True, finish=True)
             done = t.cuda.Event()
@@ -319,30 +336,34 @@ class VideoPipeline:
     def _collect(self, st):
         st.tracker.check_status()
         phases, count, state = st.lanes.read()
-        rows = st.tracker.rows_host(0)
-        # every id the tracker emitted needs a velocity lane (lane l follows id l + 1); an id past the
-        # lanes would silently get no phases and no path length -- the reference's plot.py can
-        # analyse any id (plot.py:88), so this is a capacity error, not a truncation
-        if len(rows) and int(rows[:, 0].max()) > self.id_lanes:
-            raise _lib.VbtError(_lib.ECAPACITY,
-                                f'track id {int(rows[:, 0].max())} exceeds the {self.id_lanes} velocity lanes of '
-                                f'this VideoPipeline; construct it with id_lanes >= the number of tracks born')
-        out_ph, out_path = {}, {}
-        for l in range(self.id_lanes):
-            if state[l, 2] > 0:
-                out_ph[l + 1] = _phases_from(phases[l], int(count[l]))
-                out_path[l + 1] = float(state[l, 3])
-        out = dict(rows=rows, phases=out_ph, path=out_path)
-        if self.keep_details:
-            out['details'] = st.tracker.details[0, :len(rows)].cpu().numpy()
-            t = self.torch
-            if st.frame_log:
-                nos = t.cat([a for a, _ in st.frame_log]).cpu().numpy()
-                cnt = t.cat([b for _, b in st.frame_log]).cpu().numpy()
-                out['frames_with_results'] = [int(f) for f, c in zip(nos, cnt) if c > 0]
-            else:
-                out['frames_with_results'] = []
-        return out
+        results = []
+        for v in range(self.V):
+            rows = st.tracker.rows_host(v)
+            # every id the tracker emitted needs a velocity lane (lane l follows id l + 1); an id past the
+            # lanes would silently get no phases and no path length -- the reference's plot.py can
+            # analyse any id (plot.py:88), so this is a capacity error, not a truncation
+            if len(rows) and int(rows[:, 0].max()) > self.id_lanes:
+                raise _lib.VbtError(_lib.ECAPACITY,
+                                    f'track id {int(rows[:, 0].max())} exceeds the {self.id_lanes} velocity lanes of '
+                                    f'this VideoPipeline; construct it with id_lanes >= the number of tracks born')
+            out_ph, out_path = {}, {}
+            for l in range(self.id_lanes):
+                j = v * self.id_lanes + l
+                if state[j, 2] > 0:
+                    out_ph[l + 1] = _phases_from(phases[j], int(count[j]))
+                    out_path[l + 1] = float(state[j, 3])
+            out = dict(rows=rows, phases=out_ph, path=out_path)
+            if self.keep_details:
+                out['details'] = st.tracker.details[v, :len(rows)].cpu().numpy()
+                t = self.torch
+                if st.frame_log and self.V == 1:
+                    nos = t.cat([a for a, _ in st.frame_log]).cpu().numpy()
+                    cnt = t.cat([b for _, b in st.frame_log]).cpu().numpy()
+                    out['frames_with_results'] = [int(f) for f, c in zip(nos, cnt) if c > 0]
+                else:
+                    out['frames_with_results'] = []
+            results.append(out)
+        return results[0] if self.V == 1 else results
 
 
 def rows_to_data(rows):

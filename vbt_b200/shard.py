@@ -78,7 +78,7 @@ def gather_row_tables(local_tables, n_videos, device=None, group=None):
 
 
 def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank=None, world=None,
-                 group=None, **pipe_kw):
+                 group=None, gather=True, **pipe_kw):
     """Run the hot path over many videos, sharded by whole videos across the ranks.
 
     videos: list of dicts ``{'fps': float, 'frames': uint8 [N,H,W,3] CUDA or pinned-host tensor}``
@@ -86,7 +86,8 @@ def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank
     `VideoPipeline` (tracker and velocity state reset per video, like the fresh interpreter and
     tracker per source of track.py:88-101,157), then ONE gather makes every row table visible on
     every rank.  Returns ``(tables, phases)``: tables = {video index: float64 [n,8]} for all
-    videos, phases = {video index: {id: [Phase]}} for this rank's videos."""
+    videos, phases = {video index: {id: [Phase]}} for this rank's videos.  gather=False: no
+    collective, `tables` holds this rank's videos only (a 1-rank reference run inside a larger job)."""
     import torch
     import torch.distributed as dist
     from .pipeline import VideoPipeline
@@ -122,7 +123,7 @@ def track_videos(videos, detector, detection_threshold=0.5, frame_stride=1, rank
             res = h.result()
             local[vi], phases[vi] = res['rows'], res['phases']
         local[prev], phases[prev] = last['rows'], last['phases']
-    tables = gather_row_tables(local, len(videos), group=group)
+    tables = gather_row_tables(local, len(videos), group=group) if gather else local
     return tables, phases
 
 
