@@ -62,6 +62,8 @@ struct MbArgs {
   int pj_zp, res_zp, add_mult0, add_mult1, add_shift, zp_final, lo, hi;
   int img_stride, img_bytes, off_taps, off_wproj, off_consts;
   int tmem_cols, col_pj;
+  int split, col_split, stage_stride;          // split 2: a cluster of two CTAs shares a tile's chunks (see kernel)
+  uint32_t sm_stage;
   uint32_t sm_exp, sm_mid, sm_wbuf, in_gstride, mid_gstride;   // bytes
   long long* dbg;                            // VBT_MB_DBG=1: cycle counters of CTA (0,0), threads 0 and 64
 };
@@ -126,6 +128,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t local_smem_addr, uint32_t cta) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(local_smem_addr), "r"(cta));
+  return r;
+}
+__device__ __forceinline__ void st_cluster16(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
 
 #define MB_TICK(i)                                                        \
   do {                                                                   \
@@ -204,13 +224,17 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
   constexpr int NLD = S == 1 ? 2 : 3;                 // activation words per window row and strip
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row = tid & 127, half = tid >> 7;
-  const int tile = blockIdx.x, b = blockIdx.y;
+  // split 2: the two CTAs of a cluster work on the same tile, CTA r on the chunks r, r + 2, ... ; their
+  // partial project accumulators meet through distributed shared memory at the end
+  const int split = a.split;
+  const int rank = split == 2 ? (int)cluster_ctarank() : 0;
+  const int tile = blockIdx.x / split, b = blockIdx.y;
   const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
   const int oy0 = ty * a.TH, ox0 = tx * a.TW;
   const int ey0 = oy0 * S - a.pad_top, ex0 = ox0 * S - a.pad_left;   // window origin in input coordinates
   const uint32_t s_in = smem_u32(smem), s_exp = s_in + a.sm_exp, s_mid = s_in + a.sm_mid;
   const uint32_t s_wbuf = s_in + a.sm_wbuf;
-  const int n_chunks = a.n_chunks;
+  const int n_chunks = (a.n_chunks - rank + split - 1) / split;     // this CTA's chunks (local index c)
   const uint32_t cs = (uint32_t)a.chan_stride;
   const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 64);
   long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -236,7 +260,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)a.img_bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                      "r"(s_wbuf + (uint32_t)(c % kWBuf) * a.img_stride),
-                 "l"(a.img + (size_t)c * a.img_stride), "r"((uint32_t)a.img_bytes), "r"(bar)
+                 "l"(a.img + (size_t)(rank + c * split) * a.img_stride), "r"((uint32_t)a.img_bytes), "r"(bar)
                  : "memory");
   };
   if (tid == 64) load_image(0);
@@ -444,6 +468,25 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
   if (warp == 0) mbar_wait(smem_u32(&bar_p[(n_chunks - 1) & 1]), (uint32_t)(((n_chunks - 1) >> 1) & 1));
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
+  // columns this CTA finalises; with a partner, the partner's partial sums for them arrive in `stage`
+  int col_lo = 0, col_hi = a.cout_p;
+  const uint32_t s_stage = s_in + a.sm_stage;
+  if (split == 2) {
+    col_lo = rank == 0 ? 0 : a.col_split;
+    col_hi = rank == 0 ? a.col_split : a.cout_p;
+    const int p_lo = rank == 0 ? a.col_split : 0, p_hi = rank == 0 ? a.cout_p : a.col_split;
+    cluster_sync_all();            // both CTAs are past their chunk loops: the staging areas (weight / plane buffers) are free
+    const uint32_t remote = map_to_cta(s_stage, (uint32_t)(rank ^ 1));
+    for (int t = 0; t < a.n_out_tiles; ++t)
+      for (int c0 = p_lo + half * 16; c0 < p_hi; c0 += 32) {
+        uint32_t v[16];
+        tmem_ld16(tmem + lane_base + (uint32_t)(a.col_pj + t * a.cout_p + c0), v);
+        const uint32_t dst = remote + (uint32_t)(t * 128 + row) * a.stage_stride + (uint32_t)(c0 - p_lo) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) st_cluster16(dst + j * 16, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      }
+    cluster_sync_all();            // partials delivered (release / acquire at cluster scope)
+  }
   const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
   for (int t = 0; t < a.n_out_tiles; ++t) {
     const int q = t * 128 + row;
@@ -454,9 +497,17 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
     int8_t* o = a.out + (((size_t)b * a.Ho + oy) * a.Wo + ox) * a.cout_p;
     // residual: the block input at the same pixel (stride 1), still in the input planes
     const uint32_t rpos = (uint32_t)((ly + a.pad_top) * a.WW + lx + a.pad_left) * 16;
-    for (int c0 = half * 16; c0 < a.cout_p; c0 += 32) {
+    for (int c0 = col_lo + half * 16; c0 < col_hi; c0 += 32) {
       uint32_t v[16];
       tmem_ld16(tmem + lane_base + (uint32_t)(a.col_pj + t * a.cout_p + c0), v);
+      if (split == 2) {
+        const uint32_t src = s_stage + (uint32_t)(t * 128 + row) * a.stage_stride + (uint32_t)(c0 - col_lo) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 pv = ld_shared16(src + j * 16);
+          v[4 * j] += pv.x; v[4 * j + 1] += pv.y; v[4 * j + 2] += pv.z; v[4 * j + 3] += pv.w;
+        }
+      }
       if (!valid) continue;
       uint32_t packed[4];
       uint4 rv = make_uint4(0, 0, 0, 0);
@@ -590,7 +641,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
       // CTAs that share an SM share its issue slots: two resident CTAs take ~1.7x one CTA's time
       const long long in_wave = std::min(ctas, 148LL * per_sm);
       const long long share = in_wave > 148 ? 17 : 10;
-      const long long cost = waves * cta * share / 10;
+      const long long cost = waves * cta * share / 10 * (cols_p > 256 ? 11 : 10) / 10;   // 512 columns: nothing else fits on the SM
       if (best < 0 || cost < best) { best = cost; bg = g; }
     }
   }
@@ -635,16 +686,46 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
     if (!dbg_buf) cudaMalloc(&dbg_buf, 24 * sizeof(long long));
     a.dbg = dbg_buf;
   }
-  VBT_CHECK_CUDA(launch_pdl(kern, dim3((unsigned)(a.tiles_x * tiles_y), (unsigned)B), dim3(kThreads), smem, st, a));
+  // Cluster split: when the grid leaves the GPU under-filled (one CTA per SM or fewer: the 20x20 and 10x10
+  // stages at frame batch 64), two CTAs share a tile's chunks and exchange partial sums at the end.
+  static const bool split_on = [] { const char* e = getenv("VBT_MB_SPLIT"); return !(e && e[0] == '0'); }();
+  const long long n_ctas = (long long)a.tiles_x * tiles_y * B;
+  a.split = 1; a.col_split = a.cout_p; a.stage_stride = 0; a.sm_stage = a.sm_exp;
+  const int resident = std::max(1, std::min(std::min((int)(226 * 1024 / (smem + 4096)), 512 / cols), 2));   // CTAs per SM
+  if (split_on && ex && a.n_chunks >= 4 && 2 * n_ctas <= 148LL * resident) {
+    const int col_split = (a.cout_p / 32) * 16;
+    const int stride = std::max(col_split, a.cout_p - col_split) * 4 + 16;     // + 16: rows land on different banks
+    const size_t stage = (size_t)a.n_out_tiles * 128 * stride;
+    const size_t need = (size_t)a.sm_exp + stage;
+    if (std::max(need, smem) <= 200 * 1024) {
+      a.split = 2; a.col_split = col_split; a.stage_stride = stride;
+      smem = std::max(smem, need);
+    }
+  }
+  {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(a.tiles_x * tiles_y * a.split), (unsigned)B);
+    cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    if (a.split == 2) {
+      attr[1].id = cudaLaunchAttributeClusterDimension;
+      attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
+      cfg.numAttrs = 2;
+    }
+    VBT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  }
   if (dbg) {       // debugging aid, never inside a graph capture: cycle counters of CTA (0, 0)
     long long h[24];
     cudaStreamSynchronize(st);
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* nm[12] = {"prologue+fill", "wait image", "wait E", "EE", "sync", "E issue", "-", "-",
                                  "DW+DE", "fence+sync", "P issue", "final"};
-    fprintf(stderr, "[mbconv %dx%d cin_p %d k%d s%d cout_p %d chunks %d | TH %d TW %d win_tiles %d out_tiles %d strips %d grid %d x %d tmem %d smem %zu]\n",
+    fprintf(stderr, "[mbconv %dx%d cin_p %d k%d s%d cout_p %d chunks %d | TH %d TW %d win_tiles %d out_tiles %d strips %d grid %d x %d split %d tmem %d smem %zu]\n",
             a.H, a.W, a.cin_p, K, S, a.cout_p, a.n_chunks, a.TH, a.TW, a.n_win_tiles, a.n_out_tiles, a.n_strips,
-            a.tiles_x * tiles_y, B, a.tmem_cols, smem);
+            a.tiles_x * tiles_y, B, a.split, a.tmem_cols, smem);
     for (int i = 0; i < 12; ++i) fprintf(stderr, "   %-14s t0 %8lld   t64 %8lld\n", nm[i], h[i], h[12 + i]);
   }
   *taken = true;
