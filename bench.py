@@ -238,12 +238,12 @@ def run_configs4(args, g, det, rank, world):
         torch.cuda.synchronize()
 
     # warm-up = the whole workload once (graph capture per lane, NCCL channel set-up), then the timed pass
-    shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14)
+    shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14, id_lanes=256)
     barrier()
     launches0 = _lib.lib().vbt_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    tables, _ = shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14)
+    tables, _ = shard.track_videos(videos, det, 0.5, rank=rank, world=world, row_cap=1 << 14, id_lanes=256)
     ev1.record()
     barrier()
     launches = _lib.lib().vbt_launch_count() - launches0
@@ -255,7 +255,7 @@ def run_configs4(args, g, det, rank, world):
     if rank == 0:                       # the same 34 videos on this GPU alone, no collective
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        ref, _ = shard.track_videos(videos, det, 0.5, rank=0, world=1, gather=False, row_cap=1 << 14)
+        ref, _ = shard.track_videos(videos, det, 0.5, rank=0, world=1, gather=False, row_cap=1 << 14, id_lanes=256)
         torch.cuda.synchronize()
         single = sum(counts) / (time.perf_counter() - t0)
         same = sum(1 for v in range(len(videos)) if np.array_equal(tables[v], ref[v]))
@@ -326,8 +326,8 @@ def main():
     pipe = VideoPipeline(det, FPS, 0.5, row_cap=1 << 17, n_videos=V)
     # every rank owns its own clip(s) (weak scaling: whole videos are the shard unit).
     # V > 1: V clips advance together, each batch holds B / V frames of every clip, video-major.
-    f = B // V
-    n_batches = (args.clip_frames + f - 1) // f
+    fpv = B // V                                     # frames of each video per batch
+    n_batches = (args.clip_frames + fpv - 1) // fpv
     clips = [render_clip(args.clip_frames, H, W, seed=rank * V + v, device='cuda',
                          trajectory=plate_trajectory(args.clip_frames, FPS, seed=rank * V + v)) for v in range(V)]
     if V == 1:
@@ -335,7 +335,7 @@ def main():
     else:                                            # interleave once, outside every timed region
         parts = []
         for b in range(n_batches):
-            s, e = b * f, min((b + 1) * f, args.clip_frames)
+            s, e = b * fpv, min((b + 1) * fpv, args.clip_frames)
             parts.extend(c[s:e] for c in clips)
         clip = torch.cat(parts)
         del parts
@@ -346,7 +346,7 @@ def main():
 
     def batch_range(b):
         """(first, last) frame of batch b in `clip`, and the frame numbers of its frames."""
-        s, e = b * f, min((b + 1) * f, args.clip_frames)
+        s, e = b * fpv, min((b + 1) * fpv, args.clip_frames)
         return s * V, e * V, (numbers1[s:e] if V == 1 else numbers1[s:e].repeat(V))
 
     batch_numbers = [batch_range(b)[2].contiguous() for b in range(n_batches)]
@@ -473,7 +473,7 @@ def main():
     stage_events, pipe.stage_events = pipe.stage_events, None
     pipe.active_lanes = len(pipe.detectors)
     # workload statistics of the last batch
-    dets_per_frame = float(pipe.det_count[pipe.last_slot, 0, :f * V].float().mean().item())
+    dets_per_frame = float(pipe.det_count[pipe.last_slot, 0, :fpv * V].float().mean().item())
     live_tracks = int(len(pipe.tracker.peek(0)))
 
     # ---- per-kernel breakdown + roofline of the dominant kernel ---------------------------

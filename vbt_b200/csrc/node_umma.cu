@@ -92,6 +92,16 @@ __device__ __forceinline__ uint4 s8x8_to_bf16(uint32_t w0, uint32_t w1) {
   return make_uint4(__byte_perm(f[0], f[1], 0x7632), __byte_perm(f[2], f[3], 0x7632),
                     __byte_perm(f[4], f[5], 0x7632), __byte_perm(f[6], f[7], 0x7632));
 }
+// one elected lane of a warp-uniform region issues the MMAs: under a divergent `if (tid == 0)` ptxas wraps
+// every UTCIMMA in an ELECT / R2UR / BRA.U.ANY loop (its operands live in uniform registers) -- measured
+// at ~100 cycles per instruction in csrc/mbconv_umma.cu
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0, lane = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, %2;\n\t@px mov.s32 %1, 1;\n\tmov.s32 %0, rx;\n\t}\n"
+      : "+r"(lane), "+r"(pred) : "r"(0xffffffffu));
+  return pred;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(bar)
                : "memory");
@@ -304,9 +314,11 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
   const uint32_t tmem = tmem_base_s;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
   // ---- depthwise: nine shifted views per tile and group pair ----------------------------------
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t pbase = smem_u32(pin), wbase = smem_u32(wdw);
     for (int mt = 0; mt < a.n_mt; ++mt) {
@@ -316,7 +328,7 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
           for (int kx = 0; kx < 3; ++kx, ++t) {
             const uint32_t aaddr = pbase + (uint32_t)(2 * p) * in_plane +
                                    ((uint32_t)mt * 128 + (uint32_t)(ky * a.PW + kx)) * 16;
-            umma_i8(tmem + (uint32_t)(mt * a.pairs + p) * 32, umma_desc(aaddr, in_plane, 128),
+            umma_i8(tmem_u + (uint32_t)(mt * a.pairs + p) * 32, umma_desc(aaddr, in_plane, 128),
                     umma_desc(wbase + (uint32_t)(p * 9 + t) * 1024, 512, 128), idesc, t > 0 ? 1u : 0u);
           }
       }
@@ -364,7 +376,7 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   asm volatile("tcgen05.fence::after_thread_sync;\n");
 
   // ---- pointwise ---------------------------------------------------------------------------------
-  if (tid == 0) {
+  if (warp_u == 0 && elect_one()) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.cout_p >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t abase = smem_u32(pmid), bbase = smem_u32(wpw);
     // bf16: D = F32, A = B = BF16; one MMA (K = 16 elements) per 16-channel group
@@ -372,12 +384,12 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
     for (int mt = 0; mt < a.n_mt; ++mt) {
       if (!a.pw_bf16) {
         for (int k2 = 0; k2 < Ge / 2; ++k2)
-          umma_i8(tmem + (uint32_t)mt * a.cout_p,
+          umma_i8(tmem_u + (uint32_t)mt * a.cout_p,
                   umma_desc(abase + (uint32_t)(2 * k2) * mid_plane + (uint32_t)mt * 2048, mid_plane, 128),
                   umma_desc(bbase + (uint32_t)k2 * 256, 128, (uint32_t)Ge * 128), idesc, k2 > 0 ? 1u : 0u);
       } else {
         for (int g = 0; g < G; ++g)
-          umma_f16(tmem + (uint32_t)mt * a.cout_p,
+          umma_f16(tmem_u + (uint32_t)mt * a.cout_p,
                    umma_desc(abase + (uint32_t)(2 * g) * mid_plane + (uint32_t)mt * 2048, mid_plane, 128),
                    umma_desc(bbase + (uint32_t)g * 256, 128, (uint32_t)(2 * G) * 128), idesc16, g > 0 ? 1u : 0u);
       }

@@ -77,3 +77,101 @@ class RowSparseIngest:
         ready = t.cuda.Event()
         ready.record(cs)
         return self.tables[slot], n, slot, ready
+
+
+class DecodeRing:
+    """Video file -> ring of pinned host batches, filled by a background decode thread.
+
+    replaces: the `cv2.VideoCapture` / `cap.read()` front of the reference loop (track.py:135-171).  The
+    reference decodes a frame, converts it, runs the network, then decodes the next one; here a thread
+    decodes straight INTO page-locked batch buffers (`VideoCapture.retrieve(dst)`: no staging copy)
+    while the GPU works on earlier batches, frames the stride skips are only `grab()`-bed (demuxed, not
+    colour-converted), and the consumer hands each full batch to `VideoPipeline.process`, whose
+    row-sparse DMA (RowSparseIngest) moves just the rows K1 reads.  SURVEY.md 8f rank 2, the
+    host-decode form: the GPU boxes of this pool expose no NVDEC user library (libnvcuvid is absent,
+    profiles/r2_gpu_box_video_libs.txt), so on-GPU decode cannot be built or tested here.
+
+    Frame numbering is the reference's: `frame_count` starts at 1 and counts every read attempt
+    (track.py:160-161); a frame is kept when `frame_count % stride == 0` (track.py:166).
+
+        ring = DecodeRing(path, batch=64, stride=16)
+        for frames, numbers, slot in ring:           # frames: uint8 [n,H,W,3] BGR (pinned), n <= batch
+            pipe.process(frames, numbers_on_device, swap_rb=True)
+            ring.release(slot, pipe.input_consumed)   # event after which the buffer may be refilled
+    """
+
+    def __init__(self, src, batch=64, stride=1, n_slots=3, pin=None):
+        import queue
+        import threading
+        import cv2
+        import torch
+        self.cap = cv2.VideoCapture(src)
+        if not self.cap.isOpened():
+            raise FileNotFoundError(src)
+        self.fps = self.cap.get(cv2.CAP_PROP_FPS)
+        self.W = int(self.cap.get(cv2.CAP_PROP_FRAME_WIDTH))
+        self.H = int(self.cap.get(cv2.CAP_PROP_FRAME_HEIGHT))
+        self.batch, self.stride = int(batch), int(stride)
+        pin = torch.cuda.is_available() if pin is None else pin
+        self.slots = []
+        for _ in range(n_slots):
+            t = torch.empty((self.batch, self.H, self.W, 3), dtype=torch.uint8)
+            self.slots.append(t.pin_memory() if pin else t)
+        self._views = [s.numpy() for s in self.slots]        # the decoder writes through these
+        self._free = queue.Queue()
+        self._full = queue.Queue(maxsize=n_slots)
+        for i in range(n_slots):
+            self._free.put((i, None))
+        self.frames_read = 0
+        self._error = None
+        self._thread = threading.Thread(target=self._decode, daemon=True)
+        self._thread.start()
+
+    def _decode(self):
+        try:
+            frame_count, n, numbers, slot = 0, 0, [], None
+            while True:
+                ok = self.cap.grab()
+                frame_count += 1                               # counts from 1, before the `ret` check
+                if not ok:
+                    break
+                if frame_count % self.stride:
+                    continue                                   # skipped frames are never colour-converted
+                if slot is None:
+                    slot, ev = self._free.get()
+                    if ev is not None:
+                        ev.synchronize()                       # the DMA that last read this buffer is done
+                dst = self._views[slot][n]
+                ok, out = self.cap.retrieve(dst)
+                if not ok:
+                    break
+                if out is not dst:                             # decoder returned its own buffer (size / layout change)
+                    np.copyto(dst, out)
+                numbers.append(frame_count)
+                n += 1
+                if n == self.batch:
+                    self._full.put((slot, n, numbers))
+                    n, numbers, slot = 0, [], None
+            if n:
+                self._full.put((slot, n, numbers))
+            self.frames_read = frame_count - 1
+        except Exception as e:                                 # surfaced in the consumer thread
+            self._error = e
+        finally:
+            self.cap.release()
+            self._full.put(None)
+
+    def __iter__(self):
+        while True:
+            item = self._full.get()
+            if item is None:
+                if self._error is not None:
+                    raise self._error
+                return
+            slot, n, numbers = item
+            yield self.slots[slot][:n], numbers, slot
+
+    def release(self, slot, event=None):
+        """The batch of `slot` has been handed on; `event` (torch.cuda.Event or None) marks when its
+        bytes have left host memory."""
+        self._free.put((slot, event))

@@ -92,61 +92,29 @@ def export_annotated_video(src, video_path, result, fps, frame_stride):
 def track(src, interpreter, detection_treshold, display_image_height=720, video_path=None,
           frame_stride=16, batch=64, return_pipeline_result=False):
     """Runs detection + tracking over one video file and returns the captured data."""
-    import cv2
     torch = _lib.require_cuda()
-    cap = cv2.VideoCapture(src)
-    fps = cap.get(cv2.CAP_PROP_FPS)
+    from .ingest import DecodeRing
+    # decode thread -> ring of pinned batches (ingest.DecodeRing): frames the stride skips are only
+    # demuxed, kept frames are decoded straight into page-locked memory while the GPU works
+    ring = DecodeRing(src, batch=batch, stride=frame_stride)
+    fps = ring.fps
     det = interpreter.detector if isinstance(interpreter, Interpreter) else interpreter
     if det.max_batch < batch:
         det = type(det)(interpreter.model_path, max_batch=batch)
     pipe = VideoPipeline(det, fps, detection_treshold, keep_details=video_path is not None,
                          tracker_kw=dict(max_age=MAX_AGE, iou_threshold=0.1))   # track.py:157
-    staged, numbers = [], []
-    pinned, copied = [None, None], [None, None]     # two pinned staging buffers, ping-pong
-    flushes = 0
-    frame_count = 0
-
-    def flush():
-        nonlocal flushes
-        if not staged:
-            return
-        n = len(staged)
-        h, w = staged[0].shape[:2]
-        k = flushes & 1
-        flushes += 1
-        if pinned[k] is None or pinned[k].shape[1:3] != (h, w):
-            pinned[k] = torch.empty((batch, h, w, 3), dtype=torch.uint8).pin_memory()
-        if copied[k] is not None:
-            copied[k].synchronize()                 # the H2D copy that last read this buffer is done
-        for i, f in enumerate(staged):
-            pinned[k][i].copy_(torch.from_numpy(f))
-        if flushes == 1:
-            pipe.use_row_sparse_ingest(h, w)           # host frames: send only the rows K1 reads
+    pipe.use_row_sparse_ingest(ring.H, ring.W)             # host frames: send only the rows K1 reads
+    for frames, numbers, slot in ring:
         nums = torch.as_tensor(np.asarray(numbers, dtype=np.int32), device='cuda')
         if pipe.ingest is not None:
-            pipe.process(pinned[k][:n], nums, swap_rb=True)    # cv2 frames are BGR (track.py:171)
-            copied[k] = pipe.input_consumed
-        else:
-            dev = pinned[k][:n].to('cuda', non_blocking=True)
-            copied[k] = torch.cuda.Event()
-            copied[k].record()
+            pipe.process(frames, nums, swap_rb=True)       # cv2 frames are BGR (track.py:171)
+            ring.release(slot, pipe.input_consumed)
+        else:                                              # odd row sizes: plain copy of the batch
+            dev = frames.to('cuda', non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
             pipe.process(dev, nums, swap_rb=True)
-        staged.clear()
-        numbers.clear()
-
-    while cap.isOpened():
-        ret, frame = cap.read()
-        frame_count += 1                               # counts from 1, before the ret check
-        if not ret:
-            break
-        if frame_count % frame_stride:
-            continue
-        staged.append(frame)
-        numbers.append(frame_count)
-        if len(staged) == batch:
-            flush()
-    flush()
-    cap.release()
+            ring.release(slot, done)
     result = pipe.finish()
     if video_path is not None:
         export_annotated_video(src, video_path, result, fps, frame_stride)
