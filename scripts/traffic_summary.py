@@ -9,7 +9,7 @@ import json
 import re
 import sys
 
-CLASS = [('node_umma', 'node_fused'), ('pw_persist', 'pw'), ('pw_umma', 'pw'), ('pw_dp4a', 'pw_head_out'), ('dw_umma', 'dw5'), ('dw_kernel', 'dw3'), ('stem', 'stem'),
+CLASS = [('mbconv_umma', 'mbconv_fused'), ('node_umma', 'node_fused'), ('pw_persist', 'pw'), ('pw_umma', 'pw'), ('pw_dp4a', 'pw_head_out'), ('dw_umma', 'dw5'), ('dw_kernel', 'dw3'), ('stem', 'stem'),
          ('add_kernel', 'fuse_add'), ('preprocess', 'K1_preprocess'), ('postprocess', 'K6_postprocess'),
          ('tracker_update', 'K7_tracker'), ('velocity_update', 'K8_velocity'), ('pack_detections', 'pack')]
 SCALE = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'ns': 1e-3, 'us': 1.0, 'ms': 1e3,

@@ -176,6 +176,25 @@ def mbconv_graph(h, w, cin, cexp, cout, k, stride, residual=False, seed=0, expan
     return g
 
 
+def stem_block_graph(h, w, cout, k, stride, cmid=32, seed=0):
+    """uint8 frame [h,w,3] -> STEM 3x3 s2 (3 -> cmid, ReLU6) -> DW kxk (ReLU6) -> PW(cmid -> cout): the network's
+    first block with the stem as its expand stage (csrc/mbconv_umma.cu, im2col rows of the frame)."""
+    rng = np.random.default_rng(seed)
+    g = _empty_graph(h, w, 3, 127)
+    ho, wo = E.same_pad(h, 3, 2)[0], E.same_pad(w, 3, 2)[0]
+    x = g._t(ho, wo, cmid, 'stem')
+    g.ops.append(E.Op(E.OP_STEM, [g.input], x, k=3, stride=2, act=True, name='stem'))
+    op = g.ops[-1]
+    op.q['w'] = rng.integers(-127, 128, (cmid, 3, 3, 3)).astype(np.int8)
+    _conv_q(rng, op, g, 127, -128, True, 27)
+    g.tensors[x].zp = -128
+    d = g._dw(x, k, stride, True, 'b1.dw')
+    _set_dw(rng, g, g.ops[-1], -128, -120, True)
+    g._pw(d, cout, False, 'b1.project')
+    _set_pw(rng, g, g.ops[-1], cmid, cout, -120, 9, False)
+    return g
+
+
 def random_input(g, B, seed=1):
     """(logical int8 [B,h,w,c], padded int8 [B,h,w,c_p] with the zero point in the pad)."""
     t = g.tensors[g.input]

@@ -260,6 +260,31 @@ def test_fused_mbconv_without_expand(h, w, c, cout, k, s, B):
     assert list(MG.run_gpu.last_plan) == [2, 0]
 
 
+@pytest.mark.parametrize('h,w,cout,k,s,B', [(64, 64, 16, 3, 1, 2), (97, 71, 16, 3, 1, 3), (40, 56, 24, 5, 2, 2), (320, 320, 16, 3, 1, 1),
+                                            (33, 33, 16, 5, 1, 2)])
+def test_fused_stem_block(h, w, cout, k, s, B):
+    """The network's first block with the STEM as its expand stage: uint8 frame -> 3x3 s2 conv (a K = 27 GEMM
+    over im2col rows, unsigned A operand, zero-point padding at the frame border) -> depthwise -> project, one
+    kernel.  Even / odd frame sizes move the SAME padding between the two borders."""
+    import torch
+    from vbt_b200.interpreter import Detector
+    g = MG.stem_block_graph(h, w, cout, k, s, seed=h + k)
+    rng = np.random.default_rng(h)
+    frames = rng.integers(0, 256, (B, h, w, 3), dtype=np.uint8)
+    frames[0, :2] = 255
+    frames[0, -2:] = 0
+    _, _, want = OE.run(g, frames, keep=True)
+    det = Detector(g, max_batch=B)
+    assert list(det.plan()) == [3, 0, 0] and list(det.plan_kinds()) == [1, 0, 0]
+    det.network(torch.as_tensor(frames, device='cuda'))
+    torch.cuda.synchronize()
+    t = g.tensors[g.ops[-1].out]
+    ws = det.workspace.cpu().numpy().view(np.int8)
+    got = ws[B * t.ws_offset:B * t.ws_offset + B * t.h * t.w * t.c_p].reshape(B, t.h, t.w, t.c_p)
+    assert np.array_equal(got[..., :t.c].astype(np.int16), want[g.ops[-1].out])
+    assert np.all(got[..., t.c:] == t.zp)
+
+
 def test_mbconv_unfused_path_still_matches():
     """VBT_MBCONV=0 runs the same blocks op by op (the kernels the fused one replaced)."""
     import os

@@ -53,6 +53,7 @@ struct MbArgs {
   int cin_p, g_in, ge_in, cout_p, n_chunks;
   int pad_top, pad_left;
   int has_expand, has_res;
+  int stem, img_h, img_w, stem_pad_top, stem_pad_left, stem_zp;   // expand stage = the stem conv over im2col rows of the uint8 frame
   // tile geometry: TH x TW output pixels; window WH x WW input pixels, M index m = wy * WW + wx
   int TH, TW, TWp, tiles_x, WH, WW, m_total, n_win_tiles, n_out_tiles, strips_x, n_strips;
   int row_stride, chan_stride;               // planar expanded planes: bytes per window row / per channel
@@ -213,8 +214,8 @@ __device__ __forceinline__ uint32_t byte_at(uint32_t w0, uint32_t w1, uint32_t w
   return (IDX & 3) ? (w >> (8 * (IDX & 3))) : w;
 }
 
-template <int K, int S>
-__global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
+template <int K, int S, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2];
   __shared__ uint32_t tmem_base_s;
@@ -269,7 +270,65 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
 
   // ---- fill: the tile's input window ------------------------------------------------------------------
   const uint32_t zpw = (uint32_t)(a.zp_fill & 0xff) * 0x01010101u;
-  if (a.has_expand) {              // -> position-major planes, the expand GEMM's A operand
+  if (a.stem) {
+    // the stem as the expand stage: window position (wy, wx) is a pixel of the stem's OUTPUT; its GEMM row
+    // is the 3x3x3 patch of the uint8 frame around (2 sy, 2 sx), bytes k = (ky * 3 + kx) * 3 + c in
+    // 0 .. 26 (27 .. 31 zero), split over the two 16-byte K planes.  One thread = one position.
+    const uint8_t* fin = reinterpret_cast<const uint8_t*>(a.in) + (size_t)b * a.img_h * a.img_w * 3;
+    const uint32_t zp = (uint32_t)a.stem_zp;
+    for (int m = tid; m < a.m_total; m += kThreads) {
+      const int wy = (int)__umulhi((uint32_t)m, a.inv_ww);
+      const int wx = m - wy * a.WW;
+      const int sy = ey0 + wy, sx = ex0 + wx;
+      if (sy < 0 || sy >= a.H || sx < 0 || sx >= a.W) continue;          // EE overrides these positions
+      const int iy0 = 2 * sy - a.stem_pad_top, ix0 = 2 * sx - a.stem_pad_left;
+      const uint32_t d0 = s_in + (uint32_t)m * 16, d1 = d0 + a.in_gstride;
+      // interior: the nine bytes of a patch row are contiguous in the frame -> three aligned words + one
+      // funnel shift per word; the 27 bytes are then permuted into the two 16-byte K planes in registers.
+      // (The aligned window may start up to 3 bytes early and end up to 3 bytes late: kept inside the
+      // frame buffer by sending the frame's last rows to the byte-wise path.)
+      if (iy0 >= 0 && iy0 + 3 < a.img_h && ix0 >= 0 && ix0 + 3 <= a.img_w) {
+        uint32_t A[3][3];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const uint8_t* p = fin + ((size_t)(iy0 + ky) * a.img_w + ix0) * 3;
+          const uint32_t sh = ((uint32_t)(uintptr_t)p & 3u) * 8;
+          const uint32_t* q = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+          const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+          A[ky][0] = __funnelshift_r(w0, w1, sh);          // bytes 0..3 of the row
+          A[ky][1] = __funnelshift_r(w1, w2, sh);          // bytes 4..7
+          A[ky][2] = __funnelshift_r(w2, 0u, sh);          // byte 8 (+ junk)
+        }
+        // K bytes: row0[0..8] row1[0..8] row2[0..8] 0 0 0 0 0
+        const uint32_t k0 = A[0][0], k1 = A[0][1];
+        const uint32_t k2 = __byte_perm(A[0][2], A[1][0], 0x6540);                       // r0b8 r1b0 r1b1 r1b2
+        const uint32_t k3 = __byte_perm(A[1][0], A[1][1], 0x6543);                       // r1b3 r1b4 r1b5 r1b6
+        const uint32_t k4 = __byte_perm(__byte_perm(A[1][1], A[1][2], 0x0043), A[2][0], 0x5410);   // r1b7 r1b8 r2b0 r2b1
+        const uint32_t k5 = __byte_perm(A[2][0], A[2][1], 0x5432);                       // r2b2 .. r2b5
+        const uint32_t k6 = __byte_perm(A[2][1], A[2][2], 0x0432) & 0x00ffffffu;         // r2b6 r2b7 r2b8 0
+        st_shared16(d0, make_uint4(k0, k1, k2, k3));
+        st_shared16(d1, make_uint4(k4, k5, k6, 0u));
+        continue;
+      }
+      // frame border: byte by byte, taps outside the frame carry the input zero point (TF SAME)
+#pragma unroll 1
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = iy0 + ky;
+        const bool row_ok = iy >= 0 && iy < a.img_h;
+        const uint8_t* src = fin + ((size_t)(row_ok ? iy : 0) * a.img_w + ix0) * 3;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+          const int ix = ix0 + j / 3;
+          uint32_t v = zp;
+          if (row_ok && ix >= 0 && ix < a.img_w) v = __ldg(src + j);
+          const int k = ky * 9 + j;
+          st_shared8((k >> 4 ? d1 : d0) + (uint32_t)(k & 15), v);
+        }
+      }
+#pragma unroll
+      for (int k = 27; k < 32; ++k) st_shared8(d1 + (uint32_t)(k & 15), 0u);
+    }
+  } else if (a.has_expand) {       // -> position-major planes, the expand GEMM's A operand
     const int G = a.g_in;
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
     const int items = a.m_total * G;
@@ -322,6 +381,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
 
   // D = S32, A = B = signed int8, K-major, M = 128, N = 32
   const uint32_t idesc32 = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
+  const uint32_t idesc_e = a.stem ? (idesc32 & ~(7u << 7)) : idesc32;      // the stem's A operand is UNSIGNED int8 (format 0)
   // Descriptors are built once; inside the loops a start address moves by adding (bytes >> 4) to the
   // descriptor's low word (the 14-bit address field never overflows: everything lies below 256 KB).
   // Two issuing warps: warp 0 owns P, warp 1 owns E, one elected lane each.
@@ -335,7 +395,7 @@ __global__ void __launch_bounds__(kThreads, 2) mbconv_umma_kernel(MbArgs a) {
       const uint64_t ad = e_adesc + (uint64_t)(wt * 128);
       const uint32_t d = tmem_u + (uint32_t)wt * 32;
       for (int k2 = 0; k2 < ksteps; ++k2)
-        umma_i8(d, ad + (uint64_t)(k2 * e_kstep), bd + (uint64_t)(k2 * 16), idesc32, k2 > 0 ? 1u : 0u);
+        umma_i8(d, ad + (uint64_t)(k2 * e_kstep), bd + (uint64_t)(k2 * 16), idesc_e, k2 > 0 ? 1u : 0u);
     }
     umma_commit(smem_u32(&bar_e));
   };
@@ -568,7 +628,13 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   a.pj_mult = reinterpret_cast<const float*>(m->dev_data + pj.scale_off);
   a.B = B; a.H = dw.h_in; a.W = dw.w_in; a.Ho = dw.h_out; a.Wo = dw.w_out;
   a.has_expand = ex != nullptr;
-  a.cin_p = ex ? ex->cin_p : dw.cin_p;
+  a.stem = ex && ex->type == OP_STEM;
+  a.img_h = a.img_w = a.stem_pad_top = a.stem_pad_left = a.stem_zp = 0;
+  if (a.stem) {
+    a.img_h = ex->h_in; a.img_w = ex->w_in; a.stem_pad_top = ex->pad_top; a.stem_pad_left = ex->pad_left;
+    a.stem_zp = ex->zp_in[0];
+  }
+  a.cin_p = a.stem ? 32 : (ex ? ex->cin_p : dw.cin_p);
   a.g_in = a.cin_p / 16; a.ge_in = (a.g_in + 1) / 2 * 2;
   a.cout_p = pj.cout_p;
   const int K = dw.k, S = dw.stride;
@@ -576,7 +642,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   a.has_res = pj.n_in == 2;
   if (a.cout_p > kMaxCout || a.cout_p % 16 || a.ge_in > 16 || (K != 3 && K != 5) || (S != 1 && S != 2)) return VBT_OK;
   if (!ex && (a.n_chunks != 1 || a.has_res)) return VBT_OK;
-  if (a.has_res && (S != 1 || !ex || pj.cout_p != ex->cin_p)) return VBT_OK;
+  if (a.has_res && (S != 1 || !ex || a.stem || pj.cout_p != ex->cin_p)) return VBT_OK;
   a.zp_fill = dw.zp_in[0];
   if (ex) a.ex_rq = Requant(ex->zp_out, ex->act_lo, ex->act_hi, ex->requant_fast);
   a.dw_rq = Requant(dw.zp_out, dw.act_lo, dw.act_hi, dw.requant_fast);
@@ -630,7 +696,9 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
       if (g.n_out > 2 || g.n_win > 6 || g.cols > 512 || g.smem > 200 * 1024) continue;
       int cols_p = 32;
       while (cols_p < g.cols) cols_p <<= 1;
-      const int per_sm = std::max(1, std::min(std::min((int)(226 * 1024 / (g.smem + 4096)), 512 / cols_p), 2));
+      // resident CTAs per SM: two by registers, three for tiles light enough for the 80-register build
+      const int max_res = (cols_p <= 128 && g.smem <= 72 * 1024) ? 3 : 2;
+      const int per_sm = std::max(1, std::min(std::min((int)(226 * 1024 / (g.smem + 4096)), 512 / cols_p), max_res));
       const long long ctas = (long long)B * ((a.Ho + TH - 1) / TH) * ((a.Wo + tw - 1) / tw);
       const long long waves = (ctas + 148LL * per_sm - 1) / (148LL * per_sm);
       // per-CTA cost model (~cycles): fill + per chunk (expand epilogue per window tile, planar depthwise per
@@ -640,7 +708,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
       const long long cta = 2500 + 40LL * g.n_win * a.ge_in + a.n_chunks * per_chunk + (long long)g.n_out * a.cout_p * 8;
       // CTAs that share an SM share its issue slots: two resident CTAs take ~1.7x one CTA's time
       const long long in_wave = std::min(ctas, 148LL * per_sm);
-      const long long share = in_wave > 148 ? 17 : 10;
+      const long long share = in_wave > 296 ? 22 : (in_wave > 148 ? 17 : 10);      // three resident CTAs: ~2.2x one CTA's time
       const long long cost = waves * cta * share / 10 * (cols_p > 256 ? 11 : 10) / 10;   // 512 columns: nothing else fits on the SM
       if (best < 0 || cost < best) { best = cost; bg = g; }
     }
@@ -669,14 +737,21 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   if (cols > 512 || smem > 200 * 1024) return VBT_OK;
   // never more CTAs per SM than TMEM can serve, so tcgen05.alloc never spins
   smem = std::max(smem, (size_t)228 * 1024 / (512 / cols + 1));
-  void (*kern)(MbArgs) = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1> : mbconv_umma_kernel<3, 2>)
-                                : (S == 1 ? mbconv_umma_kernel<5, 1> : mbconv_umma_kernel<5, 2>);
+  // Register budget: two CTAs per SM (111 registers) by default; tiles that need little shared memory and
+  // TMEM (the single-chunk first block) run three per SM at 80 registers -- more warps to hide the
+  // fill -> MMA -> epilogue latencies of a CTA that has only one chunk to pipeline
+  static const bool occ3_on = [] { const char* e = getenv("VBT_MB_OCC3"); return !(e && e[0] == '0'); }();
+  const bool occ3 = occ3_on && cols <= 128 && smem <= 72 * 1024;
+  void (*kern)(MbArgs);
+  if (occ3) kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 3> : mbconv_umma_kernel<3, 2, 3>)
+                          : (S == 1 ? mbconv_umma_kernel<5, 1, 3> : mbconv_umma_kernel<5, 2, 3>);
+  else kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 2> : mbconv_umma_kernel<3, 2, 2>)
+                     : (S == 1 ? mbconv_umma_kernel<5, 1, 2> : mbconv_umma_kernel<5, 2, 2>);
   static bool attr_set = false;
   if (!attr_set) {
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    VBT_CHECK_CUDA(cudaFuncSetAttribute(mbconv_umma_kernel<5, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    void (*all[8])(MbArgs) = {mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
+                              mbconv_umma_kernel<3, 1, 3>, mbconv_umma_kernel<3, 2, 3>, mbconv_umma_kernel<5, 1, 3>, mbconv_umma_kernel<5, 2, 3>};
+    for (auto k : all) VBT_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   static const bool dbg = [] { const char* e = getenv("VBT_MB_DBG"); return e && e[0] == '1'; }();

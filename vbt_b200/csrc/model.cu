@@ -176,8 +176,12 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
                 (size_t)(d.mb[0] - 1) * 256 + (size_t)d.mb[1] * d.mb[2] <= (size_t)hdr.data_bytes;
       if (ok && first < i) {
         const OpRecord& e = m->ops[first];
-        ok = e.type == OP_PW && e.n_in == 1 && e.out >= 0 && d.in[0] == e.out && readers[e.out] == 1 && e.out_kind == 0 &&
-             e.cout_p == d.cout_p && (p.n_in == 1 || p.in[1] == e.in[0]);
+        // the expand stage is a 1x1 conv -- or the network's stem (3x3 s2 on the uint8 input, run as a
+        // K = 27 GEMM over im2col rows)
+        const bool pw_e = e.type == OP_PW && e.n_in == 1 && e.out_kind == 0 && (p.n_in == 1 || p.in[1] == e.in[0]);
+        const bool stem_e = e.type == OP_STEM && e.k == 3 && e.stride == 2 && e.cout_p <= 32 && p.n_in == 1 &&
+                            e.in[0] >= 0 && m->tensors[e.in[0]].ws_offset < 0;
+        ok = (pw_e || stem_e) && e.out >= 0 && d.in[0] == e.out && readers[e.out] == 1 && e.cout_p == d.cout_p;
       } else if (ok) {
         ok = p.n_in == 1;
       }

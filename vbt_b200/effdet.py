@@ -502,6 +502,13 @@ def mbconv_runs(g):
     i = 0
     while i < n:
         e = g.ops[i]
+        if (e.type == OP_STEM and e.k == 3 and e.stride == 2 and i + 2 < n and g.tensors[e.out].c_p <= 32 and
+                e.inputs == [g.input] and readers.get(e.out, 0) == 1 and g.ops[i + 1].inputs == [e.out] and
+                dw_project(i + 1, -2) and g.ops[i + 2].residual < 0):
+            # the stem as the block's "expand" stage: a 3x3 s2 conv is a K = 27 GEMM over im2col rows
+            runs[i] = (i, i + 1, i + 2)
+            i += 3
+            continue
         if (e.type == OP_PW and e.out_kind == 0 and e.residual < 0 and e.branch == 0 and i + 2 < n and
                 readers.get(e.out, 0) == 1 and g.ops[i + 1].inputs == [e.out] and dw_project(i + 1, e.inputs[0]) and
                 g.tensors[e.inputs[0]].c_p <= 256):
@@ -550,7 +557,8 @@ def mbconv_images(cin_p, k, cout_p, e, d, p):
         m = hi - lo
         if e is not None:
             w = np.zeros((32, ge_in * 16), np.int8)
-            w[:m, :e['w'].shape[1]] = e['w'][lo:hi]
+            ew = e['w'].reshape(e['w'].shape[0], -1)      # stem: [cout][ky][kx][c] -> K = (ky * 3 + kx) * 3 + c
+            w[:m, :ew.shape[1]] = ew[lo:hi]
             kb = np.arange(ge_in * 16)
             off = ((nn[:, None] // 8) * ge_in + kb[None, :] // 16) * 128 + (nn[:, None] % 8) * 16 + kb[None, :] % 16
             out[c, off.reshape(-1)] = w.view(np.uint8).reshape(-1)
@@ -849,7 +857,7 @@ def pack_blob(g: Graph):
     # record (mb = [image offset / 256 + 1, image stride, chunks, first op of the run relative to it])
     for first, (ei, di, pi) in mbconv_runs(g).items():
         d_op = g.ops[di]
-        cin_p = g.tensors[g.ops[first].inputs[0]].c_p
+        cin_p = 32 if g.ops[first].type == OP_STEM else g.tensors[g.ops[first].inputs[0]].c_p   # stem: 27 im2col bytes -> 32
         img, stride, n_chunks = mbconv_images(cin_p, d_op.k, recs[pi]['cout_p'], conv[ei] if ei >= 0 else None,
                                               conv[di], conv[pi])
         off = put(img)
