@@ -890,8 +890,25 @@ def build_synthetic(variant='lite0', seed=1234, calib_frames=None, n_calib=4, he
     if calib_frames is None:
         from .synth import synthetic_model_inputs
         calib_frames = synthetic_model_inputs(n_calib, g.S, seed=seed + 1)
+    if variant != 'lite0':
+        calibrate_class_prior(g, calib_frames)
     quantize(g, calib_frames)
     return g
+
+
+def calibrate_class_prior(g, frames, per_frame=4.0):
+    """Shift the class head's bias so that about `per_frame` anchors per frame clear score 0.5 -- what a
+    trained single-class detector shows on these videos (1-3 plates) and what the
+    Lite0 initialisation gives by itself (3-5).  The wider / deeper Lite1 and Lite2 random heads would
+    otherwise fire on hundreds of anchors, every frame would return all 25 detections and the tracker
+    would carry ~30 live tracks: a workload no real clip produces (round-1 bench lines of configs[2]/[3]
+    were tracker-bound for that reason).  Lite0 is left exactly as it was."""
+    _, outs = float_forward(g, frames)
+    logits = np.concatenate([o.reshape(o.shape[0], -1).numpy() for o in outs[1]], axis=1)
+    t = float(np.quantile(logits, 1.0 - per_frame / logits.shape[1]))
+    for op in g.ops:
+        if op.out_kind == 1:
+            op.bias = (op.bias - np.float32(_coarse(t))).astype(np.float32)
 
 
 def anchors_only(variant='lite0', box_scale=0.05, box_zp=0):
