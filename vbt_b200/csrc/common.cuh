@@ -60,12 +60,12 @@ inline int greatest_priority() {
 
 template <typename Arg>
 cudaError_t launch_pdl(void (*kernel)(Arg), dim3 grid, dim3 block, size_t smem, cudaStream_t st, const Arg& arg,
-                       bool high_priority = false) {
+                       bool high_priority = false, bool pdl = true) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (high_priority) {
     attr[1].id = cudaLaunchAttributePriority;

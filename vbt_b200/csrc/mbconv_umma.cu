@@ -34,6 +34,10 @@
 //           planes), store.
 // MMAs are issued by one ELECTED lane of a warp-uniform region: issuing from `if (tid == 0)` makes
 // ptxas wrap every UTCIMMA in an ELECT / R2UR / BRA.U.ANY loop (~100 cycles each, measured).
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
+
+#include <string.h>
+
 #include "model.cuh"
 #include "requant.cuh"
 
@@ -63,6 +67,7 @@ struct MbArgs {
   int pj_zp, res_zp, add_mult0, add_mult1, add_shift, zp_final, lo, hi;
   int img_stride, img_bytes, off_taps, off_wproj, off_consts;
   int tmem_cols, col_pj;
+  int use_tma;                               // the input window arrives as tiled TMA loads (one per 16-channel group)
   int split, col_split, stage_stride;          // split 2: a cluster of two CTAs shares a tile's chunks (see kernel)
   uint32_t sm_stage;
   uint32_t sm_exp, sm_mid, sm_wbuf, in_gstride, mid_gstride;   // bytes
@@ -215,9 +220,9 @@ __device__ __forceinline__ uint32_t byte_at(uint32_t w0, uint32_t w1, uint32_t w
 }
 
 template <int K, int S, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a) {
+__global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2];
+  __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2], bar_in;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t sPjBias[kMaxCout];
   __shared__ __align__(16) float sPjMult[kMaxCout];
@@ -252,6 +257,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_e)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[0])));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[1])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_in)));
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   for (int i = tid; i < a.cout_p; i += kThreads) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
@@ -328,7 +334,22 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a) {
 #pragma unroll
       for (int k = 27; k < 32; ++k) st_shared8(d1 + (uint32_t)(k & 15), 0u);
     }
-  } else if (a.has_expand) {       // -> position-major planes, the expand GEMM's A operand
+  } else if (a.has_expand && a.use_tma) {
+    // -> position-major planes, the expand GEMM's A operand, by TMA: the activation tensor is described to
+    // the copy engine as [B][H][W][cin_p] bytes; one tiled load per 16-channel group drops the group's
+    // WH x WW window (16-byte rows) exactly where the plane layout wants it -- [m = wy * WW + wx][16 B] --
+    // and fills what lies outside the image with zeros (never used: EE overrides those positions).
+    if (tid == 96) {
+      const uint32_t bar = smem_u32(&bar_in);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(a.g_in * a.m_total * 16)) : "memory");
+      for (int g = 0; g < a.g_in; ++g)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(s_in + (uint32_t)g * a.in_gstride), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(g * 16), "r"(ex0), "r"(ey0), "r"(b), "r"(bar)
+            : "memory");
+    }
+    mbar_wait(smem_u32(&bar_in), 0);
+  } else if (a.has_expand) {       // the same by per-thread cp.async (VBT_MB_TMA=0, or no tensor map could be encoded)
     const int G = a.g_in;
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
     const int items = a.m_total * G;
@@ -609,6 +630,29 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a) {
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda): an int8 NHWC
+// activation tensor as a 4-D byte tensor (cin_p, W, H, B), box = (16 bytes, WW, WH, 1): one 16-channel
+// group of a tile's input window per load, 16-byte rows packed in (wy, wx) order.
+bool encode_window_map(CUtensorMap* out, const void* base, int B, int H, int W, int cin_p, int WW, int WH) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeFn)p;
+  }();
+  if (!fn) return false;
+  const cuuint64_t dims[4] = {(cuuint64_t)cin_p, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)cin_p, (cuuint64_t)W * cin_p, (cuuint64_t)H * W * cin_p};
+  const cuuint32_t box[4] = {16u, (cuuint32_t)WW, (cuuint32_t)WH, 1u};
+  const cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
+  return fn(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace
 
 namespace vbt {
@@ -677,6 +721,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
     g->smem = (size_t)a.ge_in * g->n_win * 2048 + (size_t)round_up(32 * g->chan_stride, 128) +
               (size_t)4 * (g->n_out * 2048 + 16) + (size_t)kWBuf * a.img_stride + 128;
   };
+  static const int max_cols = [] { const char* e = getenv("VBT_MB_MAXCOLS"); return e ? atoi(e) : 512; }();
   static const int env_tw = [] { const char* e = getenv("VBT_MB_TW"); return e ? atoi(e) : 0; }();
   static const int env_th = [] { const char* e = getenv("VBT_MB_TH"); return e ? atoi(e) : 0; }();
   long long best = -1;
@@ -694,6 +739,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
       Geo g;
       geo(TH, tw, &g);
       if (g.n_out > 2 || g.n_win > 6 || g.cols > 512 || g.smem > 200 * 1024) continue;
+      if (g.cols > max_cols && g.n_win * 32 + a.cout_p <= max_cols) continue;   // a narrower tile exists: keep TMEM for a co-resident CTA
       int cols_p = 32;
       while (cols_p < g.cols) cols_p <<= 1;
       // resident CTAs per SM: two by registers, three for tiles light enough for the 80-register build
@@ -742,14 +788,14 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   // fill -> MMA -> epilogue latencies of a CTA that has only one chunk to pipeline
   static const bool occ3_on = [] { const char* e = getenv("VBT_MB_OCC3"); return !(e && e[0] == '0'); }();
   const bool occ3 = occ3_on && cols <= 128 && smem <= 72 * 1024;
-  void (*kern)(MbArgs);
+  void (*kern)(MbArgs, CUtensorMap);
   if (occ3) kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 3> : mbconv_umma_kernel<3, 2, 3>)
                           : (S == 1 ? mbconv_umma_kernel<5, 1, 3> : mbconv_umma_kernel<5, 2, 3>);
   else kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 2> : mbconv_umma_kernel<3, 2, 2>)
                      : (S == 1 ? mbconv_umma_kernel<5, 1, 2> : mbconv_umma_kernel<5, 2, 2>);
   static bool attr_set = false;
   if (!attr_set) {
-    void (*all[8])(MbArgs) = {mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
+    void (*all[8])(MbArgs, CUtensorMap) = {mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
                               mbconv_umma_kernel<3, 1, 3>, mbconv_umma_kernel<3, 2, 3>, mbconv_umma_kernel<5, 1, 3>, mbconv_umma_kernel<5, 2, 3>};
     for (auto k : all) VBT_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
@@ -783,14 +829,30 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
     cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    static const bool pdl = [] { const char* e = getenv("VBT_MB_PDL"); return !(e && e[0] == '0'); }();
+    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     if (a.split == 2) {
       attr[1].id = cudaLaunchAttributeClusterDimension;
       attr[1].val.clusterDim.x = 2; attr[1].val.clusterDim.y = 1; attr[1].val.clusterDim.z = 1;
       cfg.numAttrs = 2;
     }
-    VBT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    // the input window as tiled TMA loads: the activation tensor [B][H][W][cin_p] described to the copy engine
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    static const bool tma_on = [] { const char* e = getenv("VBT_MB_TMA"); return !(e && e[0] == '0'); }();
+    a.use_tma = 0;
+    if (tma_on && ex && !a.stem && a.WW <= 256 && a.WH <= 256) {
+      static std::map<std::tuple<const void*, int, int, int, int, int, int>, CUtensorMap> maps;
+      const auto mkey = std::make_tuple((const void*)in, B, a.H, a.W, a.cin_p, a.WW, a.WH);
+      auto it = maps.find(mkey);
+      if (it == maps.end()) {
+        CUtensorMap tm;
+        if (encode_window_map(&tm, in, B, a.H, a.W, a.cin_p, a.WW, a.WH)) it = maps.emplace(mkey, tm).first;
+      }
+      if (it != maps.end()) { tmap = it->second; a.use_tma = 1; }
+    }
+    VBT_CHECK_CUDA(cudaLaunchKernelEx(&cfg, kern, a, tmap));
   }
   if (dbg) {       // debugging aid, never inside a graph capture: cycle counters of CTA (0, 0)
     long long h[24];
@@ -798,9 +860,9 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
     cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
     static const char* nm[12] = {"prologue+fill", "wait image", "wait E", "EE", "sync", "E issue", "-", "-",
                                  "DW+DE", "fence+sync", "P issue", "final"};
-    fprintf(stderr, "[mbconv %dx%d cin_p %d k%d s%d cout_p %d chunks %d | TH %d TW %d win_tiles %d out_tiles %d strips %d grid %d x %d split %d tmem %d smem %zu]\n",
+    fprintf(stderr, "[mbconv %dx%d cin_p %d k%d s%d cout_p %d chunks %d | TH %d TW %d win_tiles %d out_tiles %d strips %d grid %d x %d split %d tma %d tmem %d smem %zu]\n",
             a.H, a.W, a.cin_p, K, S, a.cout_p, a.n_chunks, a.TH, a.TW, a.n_win_tiles, a.n_out_tiles, a.n_strips,
-            a.tiles_x * tiles_y, B, a.split, a.tmem_cols, smem);
+            a.tiles_x * tiles_y, B, a.split, a.use_tma, a.tmem_cols, smem);
     for (int i = 0; i < 12; ++i) fprintf(stderr, "   %-14s t0 %8lld   t64 %8lld\n", nm[i], h[i], h[12 + i]);
   }
   *taken = true;

@@ -575,7 +575,10 @@ int launch_node_umma(const vbt_model* m, const OpRecord* add0, const OpRecord* a
   // VBT_NODE_PRIO=1: launch with the device's greatest priority (measured: no effect on the
   // two-lane pipeline, 31.7 k vs 31.9 k frames/s -- off by default)
   static const bool prio = [] { const char* e = getenv("VBT_NODE_PRIO"); return e && e[0] == '1'; }();
-  VBT_CHECK_CUDA(launch_pdl(node_umma_kernel, dim3((unsigned)a.n_bands, (unsigned)B), dim3(kThreads), smem, st, a, prio));
+  // VBT_NODE_PDL=0: no programmatic dependent launch for the node kernels (their CTAs then become resident only
+  // when the predecessor has finished, instead of holding shared memory / TMEM while they wait)
+  static const bool pdl = [] { const char* e = getenv("VBT_NODE_PDL"); return !(e && e[0] == '0'); }();
+  VBT_CHECK_CUDA(launch_pdl(node_umma_kernel, dim3((unsigned)a.n_bands, (unsigned)B), dim3(kThreads), smem, st, a, prio, pdl));
   *taken = true;
   return VBT_OK;
 }

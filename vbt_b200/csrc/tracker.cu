@@ -441,6 +441,14 @@ __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) 
 // order-preserving compaction, done here with warp ballots over 32-wide chunks so that no
 // lane ever walks a list alone; only births (rare, order-dependent slot allocation) and
 // the > 31-wide assignment fallback are serial.
+// VBT_TRK_DBG=1: cycles per phase of video 0 (lane 0), summed over the frames of every launch
+__device__ long long g_trk_dbg[12];
+__device__ int g_trk_dbg_on;
+#define TRK_TICK(i)                                                                          \
+  do {                                                                                       \
+    if (dbg) { const long long n__ = clock64(); g_trk_dbg[i] += n__ - dbg_t; dbg_t = n__; }   \
+  } while (0)
+
 __global__ void __launch_bounds__(32) tracker_update_kernel(
     Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
     const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det, int max_tracks,
@@ -450,6 +458,8 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
   __shared__ Shared sh;
   const unsigned full = 0xffffffffu;
   const int v = blockIdx.x, lane = threadIdx.x;
+  const bool dbg = g_trk_dbg_on && v == 0 && lane == 0;
+  long long dbg_t = dbg ? clock64() : 0;
   if (lane == 0) {
     unsigned char* p = dyn_smem;
     sh.dets = reinterpret_cast<double(*)[6]>(p); p += sizeof(double) * kMaxD * 6;
@@ -514,6 +524,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     }
   };
   fetch(0);
+  TRK_TICK(0);                                          // launch prologue: state -> shared memory
 
   for (int f = 0; f < nf; ++f) {
     const int nd0 = nxt_n;
@@ -535,6 +546,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         for (int j = 0; j < 6; ++j) sh.dets[pos][j] = d6[j];
       }
     }
+    TRK_TICK(1);
     // ---- predict every track, drop the ones whose box went NaN (list order kept) ---------
     int nt = vid.n_tracks;
     {
@@ -563,6 +575,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       nt = kept;
     }
     __syncwarp();
+    TRK_TICK(2);
     // ---- first association round ----------------------------------------------------
     for (int i = lane; i < nd * nt; i += 32) {
       const int d = i / nt, t = i - d * nt;
@@ -627,6 +640,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       }
     }
     __syncwarp();
+    TRK_TICK(3);
     // ---- unmatched lists (ascending), then pairs below the IoU threshold are undone and
     //      appended to both lists in pair order (upstream behaviour) ------------------------
     int n_un_d = 0, n_un_t = 0;
@@ -669,8 +683,10 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       n_pairs = __popc(mk);
     }
     __syncwarp();
+    TRK_TICK(4);
     if (lane < n_pairs) trk_update(T(vid.order[sh.pair_t[lane]]), sh.dets[sh.pair_d[lane]], prm.delta_t);
     __syncwarp();
+    TRK_TICK(5);
     // ---- second round: unmatched detections vs last observations (DIoU) --------------
     if (n_un_d > 0 && n_un_t > 0) {
       const int a_n = n_un_d, b_n = n_un_t;
@@ -742,9 +758,11 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         __syncwarp();
       }
     }
+    TRK_TICK(6);
     for (int i = lane; i < n_un_t; i += 32)
       trk_update(T(vid.order[sh.un_t[i]]), nullptr, prm.delta_t);
     __syncwarp();
+    TRK_TICK(7);
     // ---- births (slot allocation is order dependent: one lane) -----------------------------
     if (n_un_d > 0) {
       if (lane == 0) {
@@ -760,6 +778,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       nt = __shfl_sync(full, nt, 0);
       __syncwarp();
     }
+    TRK_TICK(8);
     // ---- output rows in reverse list order, then deaths -------------------------------------
     {
       const double time = (double)frame_no[(size_t)v * F + f] / vfps;     // track.py:169
@@ -826,6 +845,8 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
       if (lane == 0) vid.n_tracks = kept;
     }
     __syncwarp();
+    TRK_TICK(9);
+    if (dbg) g_trk_dbg[11] += 1;
   }
   if (lane == 0) { vid.frame_count = frame_count; row_count[v] = rc; }
   {                                                 // write the staged state back
@@ -930,6 +951,13 @@ int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* de
                   dev_rows && dev_row_count, "vbt_tracker_update: null pointer");
   VBT_REQUIRE(F > 0 && max_det > 0 && max_det <= kMaxD && row_cap > 0,
               "vbt_tracker_update: F=%d max_det=%d (<=%d) row_cap=%d", F, max_det, kMaxD, row_cap);
+  static const bool dbg = [] {
+    const char* e = getenv("VBT_TRK_DBG");
+    const int on = e && e[0] == '1';
+    if (on) cudaMemcpyToSymbol(g_trk_dbg_on, &on, sizeof(int));
+    return on != 0;
+  }();
+  (void)dbg;
   tracker_update_kernel<<<t->V, 32, shared_bytes(t->max_tracks), (cudaStream_t)stream>>>(
       t->videos, t->tracks, t->prm, dev_dets, dev_det_count, dev_frame_no, dev_fps, dev_n_frames,
       F, max_det, t->max_tracks, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count,
@@ -952,6 +980,15 @@ int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream) {
   VBT_CHECK_CUDA(cudaMemcpyAsync(host_status, t->scratch, sizeof(int32_t) * (size_t)t->V,
                                  cudaMemcpyDeviceToHost, st));
   VBT_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (getenv("VBT_TRK_DBG")) {
+    long long h[12];
+    cudaMemcpyFromSymbol(h, g_trk_dbg, sizeof(h));
+    static const char* nm[10] = {"prologue", "compact dets", "predict", "assoc 1", "unmatched lists", "update matched", "OCR round",
+                                 "update unmatched", "births", "output+deaths"};
+    const double fr = h[11] > 0 ? (double)h[11] : 1.0;
+    fprintf(stderr, "[tracker video 0: %lld frames stepped]\n", h[11]);
+    for (int i = 0; i < 10; ++i) fprintf(stderr, "   %-18s %10.0f cycles/frame\n", nm[i], (double)h[i] / fr);
+  }
   for (int v = 0; v < t->V; ++v)
     if (host_status[v] != 0) {
       if (host_status[v] == VBT_EINVAL) {

@@ -186,7 +186,12 @@ def track_video_chunks(video, detector, detection_threshold=0.5, frame_stride=1,
     keep = torch.arange(frame_stride, n_src + 1, frame_stride, dtype=torch.int32)   # 1-based (track.py:161,166)
     lo, hi = chunk_bounds(len(keep), world)[rank]
     pipe = VideoPipeline(detector, video['fps'], detection_threshold, **pipe_kw)
-    dets, counts, numbers = detect_chunk(pipe, video, keep[lo:hi], frame_stride)
+    # Rank 0 owns the first chunk: it tracks its own frames while it detects them (the tracker runs on
+    # the side stream as in a one-pass run) and contributes an empty table to the gather; the other
+    # ranks' tables then continue the same recurrence.  The recurrence itself stays sequential --
+    # ~19 us per frame on one warp, the bound of any single-video run.
+    own = rank == 0 and not result_on_all_ranks and world > 1
+    dets, counts, numbers = detect_chunk(pipe, video, keep[lo:hi], frame_stride, track=own)
     dets, counts, numbers = gather_detection_tables(dets, counts, numbers, group=group)
     if rank != 0 and not result_on_all_ranks:
         return None
@@ -194,9 +199,10 @@ def track_video_chunks(video, detector, detection_threshold=0.5, frame_stride=1,
     return pipe.finish()
 
 
-def detect_chunk(pipe, video, keep, frame_stride=1):
+def detect_chunk(pipe, video, keep, frame_stride=1, track=False):
     """K1-K6 + pack over the kept frames `keep` (1-based frame numbers, int32 tensor) of one
-    video -> this chunk's detection table on the device."""
+    video -> this chunk's detection table on the device.  track=True: the chunk also goes through
+    the tracker / velocity kernels at once and the returned table is empty."""
     B = pipe.det.max_batch
     numbers = keep.to('cuda')
     for s in range(0, len(keep), B):
@@ -207,5 +213,5 @@ def detect_chunk(pipe, video, keep, frame_stride=1):
         else:
             frames = video['frames']
             chunk = frames[idx[0]:idx[-1] + 1] if frame_stride == 1 else frames[idx.to(frames.device)]
-        pipe.process(chunk.contiguous(), numbers[s:s + B], swap_rb=True, track=False)
+        pipe.process(chunk.contiguous(), numbers[s:s + B], swap_rb=True, track=track)
     return pipe.detection_table()
