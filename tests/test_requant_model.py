@@ -46,3 +46,23 @@ def test_ties_go_to_even_before_the_zero_point(zp):
     p = np.float32(0.5)
     folded = int((np.float32(p + np.float32(12582912.0 + 1))).view(np.uint32)) - MAGIC_BITS   # zp = 1
     assert folded == 2 and int(np.rint(p)) + 1 == 1
+
+
+def test_synthetic_lite1_head_fires_like_a_trained_detector():
+    """effdet.calibrate_class_prior: the random Lite1 / Lite2 class heads are shifted so that a handful of
+    anchors per frame clear score 0.5 (a trained single-class detector on these clips shows 1-3 plates),
+    not hundreds; Lite0 is left as initialised."""
+    import numpy as np
+    from oracle import effdet as OE
+    from vbt_b200 import effdet as E
+    from vbt_b200.synth import synthetic_model_inputs
+    g = E.build_synthetic('lite1')
+    x = synthetic_model_inputs(2, g.S, seed=77)
+    cls, _, _ = OE.run(g, x)
+    above = (cls.astype(np.int32) + 128 >= 128).sum(axis=1)          # post-LOGISTIC score >= 0.5
+    assert np.all(above >= 1) and np.all(above <= 60), above
+    g0 = E.Graph('lite0')
+    E.init_weights(g0, 1234)
+    b_before = [op.bias.copy() for op in g0.ops if op.out_kind == 1]
+    g0b = E.build_synthetic('lite0')
+    assert all(np.array_equal(a, op.bias) for a, op in zip(b_before, [o for o in g0b.ops if o.out_kind == 1]))
