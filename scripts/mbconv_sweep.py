@@ -41,7 +41,7 @@ if len(sys.argv) > 1 and sys.argv[1] == 'child':
     print('RES ' + ' '.join(f'{v:.1f}' for v in out))
     sys.exit(0)
 
-pairs = [(0, 0)] + [(tw, th) for tw in (4, 8, 12, 16, 20, 24, 32, 40) for th in (1, 2, 3, 4, 5, 6, 8, 10, 12, 16)]
+pairs = [(0, 0)] + [(tw, th) for tw in (8, 12, 16, 20, 24, 32) for th in (4, 6, 8, 10, 16)]
 best = [(1e9, None)] * len(BLOCKS)
 for tw, th in pairs:
     env = dict(os.environ)

@@ -38,6 +38,8 @@
 
 #include <string.h>
 
+#include <utility>
+
 #include "model.cuh"
 #include "requant.cuh"
 
@@ -46,7 +48,7 @@ namespace {
 using vbt::OpRecord;
 
 constexpr int kThreads = 256;      // 8 warps: warp w owns TMEM lanes 32 * (w % 4) .., 16-channel half w / 4
-constexpr int kWBuf = 3;           // weight-image buffers
+constexpr int kWBuf = 4;           // weight-image buffers: images are requested two chunks ahead
 constexpr int kMaxCout = 352;
 
 struct MbArgs {
@@ -63,6 +65,8 @@ struct MbArgs {
   int row_stride, chan_stride;               // planar expanded planes: bytes per window row / per channel
   uint32_t inv_ww, inv_twp, inv_gin, inv_sx; // ceil(2^32 / d)
   int zp_fill;                               // zero point of the depthwise input (padding value)
+  int ee_mode;                               // experiment switches (VBT_MB_EE)
+  int ex_off, ex_span, ex_ulo;               // expand epilogue, packed clamp: relu(min(bits + ex_off, ex_span)) + ex_ulo = value + 128
   vbt::Requant ex_rq, dw_rq, pj_rq;
   int pj_zp, res_zp, add_mult0, add_mult1, add_shift, zp_final, lo, hi;
   int img_stride, img_bytes, off_taps, off_wproj, off_consts;
@@ -196,11 +200,99 @@ __device__ __forceinline__ uint32_t ld_shared32(uint32_t addr) {
 __device__ __forceinline__ void st_shared8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(addr), "r"(v));
 }
-// the 16 bytes of one position's channel group -> 16 channel planes (byte address `dst` of channel 0)
-__device__ __forceinline__ void scatter16(uint32_t dst, uint32_t cs, uint4 o) {
-  const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const int (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, "
+      "%14, %15, %16};\n" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+      "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
+}
+// The expanded tensor lives in shared memory as bytes [window row][channel 0..31][cs bytes of that row]:
+// four horizontally adjacent positions of ONE channel are a word (what the depthwise wants), and the 16
+// channels of a position lie a fixed `cs` apart.  The bytes are stored UNSIGNED (value + 128): the expand
+// epilogue's clamp then ends in [0, hi - lo] with nothing left to add, and the depthwise multiplies with
+// dp4a.u32.s32 against a bias that carries - 128 * sum(w) (effdet.mbconv_images).
+// 16 values (low bytes of 16 registers) of one position -> its 16 channel rows.  cs is a template parameter
+// so that the 16 stores share one address register (cs = 8 k + 4: an odd number of words, so that lanes =
+// channels of the depthwise hit 32 different banks).
+// CS > 0: compile-time channel stride (the 16 stores share one address register: the offsets are immediates);
+// CS == 0: `cs` at run time
+template <int OFF>
+__device__ __forceinline__ void st_shared8_imm(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u8 [%0+%2], %1;\n" ::"r"(addr), "r"(v), "n"(OFF));
+}
+template <int CS, int... J>
+__device__ __forceinline__ void scatter16_imm(uint32_t dst, const uint32_t (&u)[16], std::integer_sequence<int, J...>) {
+  (st_shared8_imm<J * CS>(dst, u[J]), ...);
+}
+template <int CS>
+__device__ __forceinline__ void scatter16(uint32_t dst, uint32_t cs, const uint32_t (&u)[16]) {
+  if (CS) {
+    scatter16_imm<CS>(dst, u, std::make_integer_sequence<int, 16>());
+  } else {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) st_shared8(dst + (uint32_t)j * cs, w[j >> 2] >> (8 * (j & 3)));
+    for (int j = 0; j < 16; ++j) st_shared8(dst + (uint32_t)j * cs, u[j]);
+  }
+}
+struct EeCtx {
+  uint32_t tmem;                 // this thread's TMEM row, first of its 16 columns
+  uint32_t dst;                  // its 16 channels' rows in the expanded planes (shared-memory address)
+  const uint32_t* pos;           // &sPos[0][row]
+  int n_win, wt0, wt_step;
+  uint32_t window_mask, inside_mask, zpu;
+  int off, span, ulo, fast, store_next;
+};
+// Expand epilogue of one chunk: accumulators (bias included) of this thread's window positions -> requantise,
+// ReLU6 -> unsigned bytes in the 16 channel rows.  Fast path per value: I2F, FMUL, half a FADD2 (round by magic
+// add: the integer lands in the low mantissa bits), ONE add-min-relu on those bits =
+// clamp(round, lo - zp, hi - zp) - (lo - zp), which IS the stored byte when lo = -128, and the byte store.
+// Positions outside the image take the zero point (TF SAME pads the depthwise INPUT): a select after the
+// arithmetic, entered only by warps that hold such a position -- no divergent second path.
+template <int CS>
+__device__ __forceinline__ void ee_tiles(const EeCtx& e, const vbt::Requant& rq, const float (&em)[16], const int (&eb_next)[16],
+                                         uint32_t cs = 0) {
+  for (int wt = e.wt0; wt < e.n_win; wt += e.wt_step) {
+    uint32_t v[16];
+    tmem_ld16(e.tmem + (uint32_t)(wt * 32), v);
+    // the accumulators are in registers: the next chunk's bias takes their place at once, so that the store's
+    // latency hides under this tile's arithmetic (completion is awaited once, after the last tile)
+    if (e.store_next) tmem_st16(e.tmem + (uint32_t)(wt * 32), eb_next);
+    const bool inside = (e.inside_mask >> wt) & 1u;
+    const bool all_inside = __all_sync(0xffffffffu, inside);
+    const uint32_t dst = e.dst + e.pos[wt * 128];
+    uint32_t u[16];
+    if (e.fast) {
+#pragma unroll
+      for (int j = 0; j < 16; j += 2) {
+        const float p0 = __fmul_rn(__int2float_rn((int)v[j]), em[j]), p1 = __fmul_rn(__int2float_rn((int)v[j + 1]), em[j + 1]);
+        unsigned long long q, mg;
+        uint32_t b0, b1;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(q) : "f"(p0), "f"(p1));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(mg) : "f"(vbt::kRoundMagic));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(q) : "l"(mg));
+        asm("mov.b64 {%0, %1}, %2;" : "=r"(b0), "=r"(b1) : "l"(q));
+        u[j] = (uint32_t)__viaddmin_s32_relu((int)b0, e.off, e.span);
+        u[j + 1] = (uint32_t)__viaddmin_s32_relu((int)b1, e.off, e.span);
+      }
+      if (e.ulo) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) u[j] += (uint32_t)e.ulo;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) u[j] = (uint32_t)(rq((int)v[j], em[j]) + 128);
+    }
+    if (!all_inside) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) u[j] = inside ? u[j] : e.zpu;
+    }
+    if ((e.window_mask >> wt) & 1u) scatter16<CS>(dst, cs, u);
+  }
+}
+// dp4a with unsigned activation bytes and signed weight bytes
+__device__ __forceinline__ int dp4a_us(uint32_t x, uint32_t w, int acc) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;\n" : "=r"(d) : "r"(x), "r"(w), "r"(acc));
+  return d;
 }
 // bytes OFF .. OFF + 3 of the byte string (w0, w1, w2)
 template <int OFF>
@@ -220,16 +312,18 @@ __device__ __forceinline__ uint32_t byte_at(uint32_t w0, uint32_t w1, uint32_t w
 }
 
 template <int K, int S, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, const __grid_constant__ CUtensorMap tmap) {
+__global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kernel(MbArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2], bar_in;
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) int32_t sPjBias[kMaxCout];
   __shared__ __align__(16) float sPjMult[kMaxCout];
+  __shared__ uint32_t sPos[6][128];                   // byte offset of window position (tile, row) inside a channel's rows
+  constexpr int NT = MINB == 1 ? 512 : 256;           // MINB == 1: sixteen warps, for tiles that leave room for one CTA per SM only
   constexpr int NWW = K == 5 ? 2 : 1;                 // weight words per window row
   constexpr int NLD = S == 1 ? 2 : 3;                 // activation words per window row and strip
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int row = tid & 127, half = tid >> 7;
+  const int row = tid & 127, half = (tid >> 7) & 1, tgrp = tid >> 8;     // tgrp: which tiles this half of a 512-thread CTA takes
   // split 2: the two CTAs of a cluster work on the same tile, CTA r on the chunks r, r + 2, ... ; their
   // partial project accumulators meet through distributed shared memory at the end
   const int split = a.split;
@@ -260,8 +354,12 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_in)));
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
-  for (int i = tid; i < a.cout_p; i += kThreads) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
-  __syncthreads();                 // barriers initialised before anyone arms or polls them
+  for (int i = tid; i < a.cout_p; i += NT) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();                 // barriers initialised before anyone arms or polls them; TMEM base published
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   auto load_image = [&](int c) {   // one thread: one bulk copy (TMA engine) of chunk c's weight image
     const uint32_t bar = smem_u32(&bar_w[c % kWBuf]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)a.img_bytes) : "memory");
@@ -270,19 +368,19 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
                  "l"(a.img + (size_t)(rank + c * split) * a.img_stride), "r"((uint32_t)a.img_bytes), "r"(bar)
                  : "memory");
   };
-  if (tid == 64) load_image(0);
+  if (tid == 64) { load_image(0); if (n_chunks > 1) load_image(1); }
   vbt::pdl_wait();
   vbt::pdl_launch_dependents();
 
   // ---- fill: the tile's input window ------------------------------------------------------------------
-  const uint32_t zpw = (uint32_t)(a.zp_fill & 0xff) * 0x01010101u;
+  const uint32_t zpu = (uint32_t)((a.zp_fill + 128) & 0xff);     // the padding value as stored (unsigned)
   if (a.stem) {
     // the stem as the expand stage: window position (wy, wx) is a pixel of the stem's OUTPUT; its GEMM row
     // is the 3x3x3 patch of the uint8 frame around (2 sy, 2 sx), bytes k = (ky * 3 + kx) * 3 + c in
     // 0 .. 26 (27 .. 31 zero), split over the two 16-byte K planes.  One thread = one position.
     const uint8_t* fin = reinterpret_cast<const uint8_t*>(a.in) + (size_t)b * a.img_h * a.img_w * 3;
     const uint32_t zp = (uint32_t)a.stem_zp;
-    for (int m = tid; m < a.m_total; m += kThreads) {
+    for (int m = tid; m < a.m_total; m += NT) {
       const int wy = (int)__umulhi((uint32_t)m, a.inv_ww);
       const int wx = m - wy * a.WW;
       const int sy = ey0 + wy, sx = ex0 + wx;
@@ -348,12 +446,11 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
             ::"r"(s_in + (uint32_t)g * a.in_gstride), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(g * 16), "r"(ex0), "r"(ey0), "r"(b), "r"(bar)
             : "memory");
     }
-    mbar_wait(smem_u32(&bar_in), 0);
   } else if (a.has_expand) {       // the same by per-thread cp.async (VBT_MB_TMA=0, or no tensor map could be encoded)
     const int G = a.g_in;
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
     const int items = a.m_total * G;
-    for (int i = tid; i < items; i += kThreads) {
+    for (int i = tid; i < items; i += NT) {
       const int m = G == 1 ? i : (int)__umulhi((uint32_t)i, a.inv_gin);   // ceil(2^32 / 1) does not fit
       const int g = i - m * G;                          // groups fastest: 16 B x G contiguous in global
       const int wy = (int)__umulhi((uint32_t)m, a.inv_ww);
@@ -366,15 +463,21 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
     }
   } else {                         // no expand conv: the input IS the depthwise input -> channel planes
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
-    for (int i = tid; i < a.m_total * 2; i += kThreads) {
+    for (int i = tid; i < a.m_total * 2; i += NT) {
       const int m = i >> 1, g = i & 1;
       const int wy = (int)__umulhi((uint32_t)m, a.inv_ww);
       const int wx = m - wy * a.WW;
       const int iy = ey0 + wy, ix = ex0 + wx;
-      uint4 v = make_uint4(zpw, zpw, zpw, zpw);
-      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && g < a.g_in)
-        v = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.cin_p + g * 16));
-      scatter16(s_exp + (uint32_t)(g * 16) * cs + (uint32_t)(wy * a.row_stride + wx), cs, v);
+      uint32_t u[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) u[j] = zpu;
+      if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W && g < a.g_in) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(fin + ((size_t)iy * a.W + ix) * a.cin_p + g * 16));
+        const uint32_t w[4] = {v.x ^ 0x80808080u, v.y ^ 0x80808080u, v.z ^ 0x80808080u, v.w ^ 0x80808080u};
+#pragma unroll
+        for (int j = 0; j < 16; ++j) u[j] = w[j >> 2] >> (8 * (j & 3));
+      }
+      scatter16<0>(s_exp + (uint32_t)(g * 16) * cs + (uint32_t)(wy * a.row_stride + wx), cs, u);
     }
   }
   // which of this thread's window positions (row of every window tile) lie inside the image / the window
@@ -386,6 +489,17 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
     const int iy = ey0 + wy, ix = ex0 + wx;
     if (m < a.m_total) window_mask |= 1u << wt;
     if (iy >= 0 && iy < a.H && ix >= 0 && ix < a.W) inside_mask |= 1u << wt;
+    if (half == 0 && tgrp == 0) sPos[wt][row] = (uint32_t)(wy * a.row_stride + wx);
+  }
+  // the expand accumulators start from the bias: every thread stores its 16 channels' bias of chunk 0 into its
+  // TMEM row of every window tile, and the expand MMAs always accumulate
+  if (a.has_expand) {
+    mbar_wait(smem_u32(&bar_w[0]), 0);
+    int eb[16];
+    load16(s_wbuf + a.off_consts + half * 64, eb);
+    for (int wt = tgrp; wt < a.n_win_tiles; wt += NT / 256) tmem_st16(tmem + lane_base + (uint32_t)(wt * 32 + half * 16), eb);
+    asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+    if (a.use_tma && !a.stem) mbar_wait(smem_u32(&bar_in), 0);
   }
   asm volatile("cp.async.commit_group;\n");
   asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -393,8 +507,6 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   // the issuing warps see their own index and the TMEM base as warp-uniform values
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -416,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
       const uint64_t ad = e_adesc + (uint64_t)(wt * 128);
       const uint32_t d = tmem_u + (uint32_t)wt * 32;
       for (int k2 = 0; k2 < ksteps; ++k2)
-        umma_i8(d, ad + (uint64_t)(k2 * e_kstep), bd + (uint64_t)(k2 * 16), idesc_e, k2 > 0 ? 1u : 0u);
+        umma_i8(d, ad + (uint64_t)(k2 * e_kstep), bd + (uint64_t)(k2 * 16), idesc_e, 1u);   // onto the bias
     }
     umma_commit(smem_u32(&bar_e));
   };
@@ -436,40 +548,56 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
   for (int c = 0; c < n_chunks; ++c) {
     const uint32_t wb = s_wbuf + (uint32_t)(c % kWBuf) * a.img_stride;
     const uint32_t consts = wb + a.off_consts;
-    // Buffer reuse: weight buffer (c + 1) % 3 last held chunk c - 2 and middle buffer c & 1 was last
+    // Buffer reuse: weight buffer (c + 2) % 4 last held chunk c - 2 and middle buffer c & 1 was last
     // read by P(c - 2): both are free once P(c - 2) has completed (E(c - 2) did long ago).
     if (warp_u == 2) {
       if (c >= 2) mbar_wait(smem_u32(&bar_p[c & 1]), (uint32_t)(((c - 2) >> 1) & 1));
-      if (c + 1 < n_chunks && elect_one()) load_image(c + 1);
+      if (c + 2 < n_chunks && elect_one()) load_image(c + 2);
     }
-    mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));     // image c visible to every thread
+    // images c and c + 1 (its expand bias is stored at the end of this chunk's epilogue): ONE warp polls the
+    // barriers, the block barrier below hands the visibility on (image c + 1 was requested a chunk ago)
+    if (!a.has_expand) mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));
     MB_TICK(1);
     // ---- EE: expand epilogue -> the chunk's expanded tensor, channel-planar ----------------------------
     if (a.has_expand) {
-      if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
+      if (a.ee_mode & 2) {
+        mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));
+        if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
+        if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
+      } else if (warp == 0) {
+        if (c == 0) mbar_wait(smem_u32(&bar_w[0]), 0);
+        if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
+        mbar_wait(smem_u32(&bar_e), par_e);
+      }
       __syncthreads();
       par_e ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;\n");
       MB_TICK(2);
-      int eb[16];
       float em[16];
-      load16(consts + half * 64, eb);
+      int eb[16];                      // the NEXT chunk's bias (image c + 1 is here: warp 0 saw its barrier before the block barrier)
       load16(consts + 128 + half * 64, em);
-      for (int wt = 0; wt < a.n_win_tiles; ++wt) {
-        uint32_t v[16];
-        tmem_ld16(tmem + lane_base + (uint32_t)(wt * 32 + half * 16), v);
-        if (!((window_mask >> wt) & 1u)) continue;
-        uint4 o = make_uint4(zpw, zpw, zpw, zpw);
-        if ((inside_mask >> wt) & 1u) {
-          int acc[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = (int)v[j] + eb[j];
-          o = requant16r(acc, a.ex_rq, em);
+      load16(s_wbuf + (uint32_t)((c + 1) % kWBuf) * a.img_stride + a.off_consts + half * 64, eb);
+      {
+        EeCtx e;
+        e.tmem = tmem + lane_base + (uint32_t)(half * 16); e.dst = s_exp + (uint32_t)(half * 16) * cs;
+        e.pos = &sPos[0][row]; e.n_win = a.n_win_tiles; e.wt0 = tgrp; e.wt_step = NT / 256;
+        e.window_mask = window_mask; e.inside_mask = inside_mask; e.zpu = zpu;
+        e.off = a.ex_off; e.span = a.ex_span; e.ulo = a.ex_ulo; e.fast = a.ex_rq.fast; e.store_next = c + 1 < n_chunks;
+        switch ((a.ee_mode & 1) ? 0u : cs) {
+          case 12: ee_tiles<12>(e, a.ex_rq, em, eb); break;
+          case 20: ee_tiles<20>(e, a.ex_rq, em, eb); break;
+          case 28: ee_tiles<28>(e, a.ex_rq, em, eb); break;
+          case 36: ee_tiles<36>(e, a.ex_rq, em, eb); break;
+          case 44: ee_tiles<44>(e, a.ex_rq, em, eb); break;
+          case 52: ee_tiles<52>(e, a.ex_rq, em, eb); break;
+          case 60: ee_tiles<60>(e, a.ex_rq, em, eb); break;
+          case 68: ee_tiles<68>(e, a.ex_rq, em, eb); break;
+          case 76: ee_tiles<76>(e, a.ex_rq, em, eb); break;
+          case 84: ee_tiles<84>(e, a.ex_rq, em, eb); break;
+          default: ee_tiles<0>(e, a.ex_rq, em, eb, cs);
         }
-        const int m = wt * 128 + row;
-        const int wy = (int)__umulhi((uint32_t)m, a.inv_ww);
-        scatter16(s_exp + (uint32_t)(half * 16) * cs + (uint32_t)(wy * a.row_stride + (m - wy * a.WW)), cs, o);
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;\n");
     }
     MB_TICK(3);
@@ -493,7 +621,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
       const float dmult = __uint_as_float(ld_shared32(consts + 384 + lane * 4));
       const uint32_t cbase = s_exp + (uint32_t)lane * cs;
       const uint32_t mbase = s_mid + (uint32_t)(c & 1) * mid_buf + (uint32_t)(lane >> 4) * a.mid_gstride + (uint32_t)(lane & 15);
-      for (int sidx = warp; sidx < a.n_strips; sidx += kThreads / 32) {
+      for (int sidx = warp; sidx < a.n_strips; sidx += NT / 32) {
         const int ly = a.strips_x == 1 ? sidx : (int)__umulhi((uint32_t)sidx, a.inv_sx);
         const int x0 = (sidx - ly * a.strips_x) * 4;
         int acc[4] = {dbias, dbias, dbias, dbias};
@@ -503,15 +631,15 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
           const uint32_t w0 = ld_shared32(raddr), w1 = ld_shared32(raddr + 4);
           const uint32_t w2 = NLD == 3 ? ld_shared32(raddr + 8) : 0u;
           raddr += (uint32_t)a.row_stride;
-          acc[0] = __dp4a((int)window<0>(w0, w1, w2), (int)wk[ky][0], acc[0]);
-          acc[1] = __dp4a((int)window<S>(w0, w1, w2), (int)wk[ky][0], acc[1]);
-          acc[2] = __dp4a((int)window<2 * S>(w0, w1, w2), (int)wk[ky][0], acc[2]);
-          acc[3] = __dp4a((int)window<3 * S>(w0, w1, w2), (int)wk[ky][0], acc[3]);
+          acc[0] = dp4a_us(window<0>(w0, w1, w2), wk[ky][0], acc[0]);
+          acc[1] = dp4a_us(window<S>(w0, w1, w2), wk[ky][0], acc[1]);
+          acc[2] = dp4a_us(window<2 * S>(w0, w1, w2), wk[ky][0], acc[2]);
+          acc[3] = dp4a_us(window<3 * S>(w0, w1, w2), wk[ky][0], acc[3]);
           if (K == 5) {
-            acc[0] = __dp4a((int)byte_at<4>(w0, w1, w2), (int)wk[ky][NWW - 1], acc[0]);
-            acc[1] = __dp4a((int)byte_at<S + 4>(w0, w1, w2), (int)wk[ky][NWW - 1], acc[1]);
-            acc[2] = __dp4a((int)byte_at<2 * S + 4>(w0, w1, w2), (int)wk[ky][NWW - 1], acc[2]);
-            acc[3] = __dp4a((int)byte_at<3 * S + 4>(w0, w1, w2), (int)wk[ky][NWW - 1], acc[3]);
+            acc[0] = dp4a_us(byte_at<4>(w0, w1, w2), wk[ky][NWW - 1], acc[0]);
+            acc[1] = dp4a_us(byte_at<S + 4>(w0, w1, w2), wk[ky][NWW - 1], acc[1]);
+            acc[2] = dp4a_us(byte_at<2 * S + 4>(w0, w1, w2), wk[ky][NWW - 1], acc[2]);
+            acc[3] = dp4a_us(byte_at<3 * S + 4>(w0, w1, w2), wk[ky][NWW - 1], acc[3]);
           }
         }
         const uint32_t y4 = a.dw_rq.fast ? a.dw_rq.pack4t<true>(acc[0], acc[1], acc[2], acc[3], dmult, dmult, dmult, dmult)
@@ -558,7 +686,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
     const int p_lo = rank == 0 ? a.col_split : 0, p_hi = rank == 0 ? a.cout_p : a.col_split;
     cluster_sync_all();            // both CTAs are past their chunk loops: the staging areas (weight / plane buffers) are free
     const uint32_t remote = map_to_cta(s_stage, (uint32_t)(rank ^ 1));
-    for (int t = 0; t < a.n_out_tiles; ++t)
+    for (int t = tgrp; t < a.n_out_tiles; t += NT / 256)
       for (int c0 = p_lo + half * 16; c0 < p_hi; c0 += 32) {
         uint32_t v[16];
         tmem_ld16(tmem + lane_base + (uint32_t)(a.col_pj + t * a.cout_p + c0), v);
@@ -569,7 +697,7 @@ __global__ void __launch_bounds__(kThreads, MINB) mbconv_umma_kernel(MbArgs a, c
     cluster_sync_all();            // partials delivered (release / acquire at cluster scope)
   }
   const int round = 1 << (a.add_shift > 0 ? a.add_shift - 1 : 0);
-  for (int t = 0; t < a.n_out_tiles; ++t) {
+  for (int t = tgrp; t < a.n_out_tiles; t += NT / 256) {
     const int q = t * 128 + row;
     const int ly = (int)__umulhi((uint32_t)q, a.inv_twp);
     const int lx = q - ly * a.TWp;
@@ -688,7 +816,15 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   if (!ex && (a.n_chunks != 1 || a.has_res)) return VBT_OK;
   if (a.has_res && (S != 1 || !ex || a.stem || pj.cout_p != ex->cin_p)) return VBT_OK;
   a.zp_fill = dw.zp_in[0];
-  if (ex) a.ex_rq = Requant(ex->zp_out, ex->act_lo, ex->act_hi, ex->requant_fast);
+  static const int ee_mode = [] { const char* e = getenv("VBT_MB_EE"); return e ? atoi(e) : 0; }();
+  a.ee_mode = ee_mode;
+  a.ex_off = a.ex_span = a.ex_ulo = 0;
+  if (ex) {
+    a.ex_rq = Requant(ex->zp_out, ex->act_lo, ex->act_hi, ex->requant_fast);
+    a.ex_off = -(kRoundMagicBits + (ex->act_lo - ex->zp_out));
+    a.ex_span = ex->act_hi - ex->act_lo;
+    a.ex_ulo = ex->act_lo + 128;
+  }
   a.dw_rq = Requant(dw.zp_out, dw.act_lo, dw.act_hi, dw.requant_fast);
   a.pj_rq = a.has_res ? Requant(pj.zp_out, -128, 127) : Requant(pj.zp_out, pj.act_lo, pj.act_hi, pj.requant_fast);
   a.pj_zp = pj.zp_out; a.res_zp = pj.zp_in[1];
@@ -714,11 +850,13 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
     g->n_win = ex ? (g->m_total + 127) / 128 : 0;
     g->n_out = (TH * g->TWp + 127) / 128;
     g->strips_x = g->TWp / 4;
-    g->row_stride = round_up(std::max(g->WW, (g->strips_x - 1) * 4 * S + nld * 4), 4);
-    g->chan_stride = g->WH * g->row_stride;
-    if ((g->chan_stride / 4) % 2 == 0) g->chan_stride += 4;       // odd word stride: lanes = channels hit 32 banks
+    // expanded tensor: [window row][channel][chan_stride bytes]; an odd number of words between channels, so that
+    // lanes = channels of the depthwise hit 32 different banks
+    g->chan_stride = round_up(std::max(g->WW, (g->strips_x - 1) * 4 * S + nld * 4), 4);
+    if ((g->chan_stride / 4) % 2 == 0) g->chan_stride += 4;
+    g->row_stride = 32 * g->chan_stride + 36;          // + 9 words: a warp of the epilogue that spans two window rows hits different banks
     g->cols = g->n_win * 32 + g->n_out * a.cout_p;
-    g->smem = (size_t)a.ge_in * g->n_win * 2048 + (size_t)round_up(32 * g->chan_stride, 128) +
+    g->smem = (size_t)a.ge_in * g->n_win * 2048 + (size_t)round_up(g->WH * g->row_stride, 128) +
               (size_t)4 * (g->n_out * 2048 + 16) + (size_t)kWBuf * a.img_stride + 128;
   };
   static const int max_cols = [] { const char* e = getenv("VBT_MB_MAXCOLS"); return e ? atoi(e) : 512; }();
@@ -751,7 +889,10 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
       // strip, barriers) + final epilogue; two CTAs sharing an SM share its issue slots
       const long long strips = (long long)TH * g.strips_x;
       const long long per_chunk = 450 + 430LL * g.n_win + (strips + 7) / 8 * (K == 5 ? 140 : 70);
-      const long long cta = 2500 + 40LL * g.n_win * a.ge_in + a.n_chunks * per_chunk + (long long)g.n_out * a.cout_p * 8;
+      // under-filled grids run as clusters of two CTAs that share a tile's chunks (below): half the chunk loop, plus the exchange
+      const bool will_split = ex && a.n_chunks >= 4 && 2 * ctas <= 148LL * std::min(per_sm, 2);
+      const long long my_chunks = will_split ? (a.n_chunks + 1) / 2 : a.n_chunks;
+      const long long cta = 2500 + 40LL * g.n_win * a.ge_in + my_chunks * per_chunk + (long long)g.n_out * a.cout_p * (will_split ? 14 : 8);
       // CTAs that share an SM share its issue slots: two resident CTAs take ~1.7x one CTA's time
       const long long in_wave = std::min(ctas, 148LL * per_sm);
       const long long share = in_wave > 296 ? 22 : (in_wave > 148 ? 17 : 10);      // three resident CTAs: ~2.2x one CTA's time
@@ -773,7 +914,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   a.in_gstride = (uint32_t)a.n_win_tiles * 2048;
   a.mid_gstride = (uint32_t)a.n_out_tiles * 2048 + 16;   // + 16: the two groups' planes land on different banks
   a.sm_exp = (uint32_t)a.ge_in * a.in_gstride * (ex ? 1 : 0);
-  a.sm_mid = a.sm_exp + (uint32_t)round_up(32 * a.chan_stride, 128);
+  a.sm_mid = a.sm_exp + (uint32_t)round_up(a.WH * a.row_stride, 128);
   a.sm_wbuf = (uint32_t)round_up((int)(a.sm_mid + 4 * a.mid_gstride), 128);
   size_t smem = (size_t)a.sm_wbuf + (size_t)kWBuf * a.img_stride;
   a.col_pj = a.n_win_tiles * 32;
@@ -788,15 +929,21 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   // fill -> MMA -> epilogue latencies of a CTA that has only one chunk to pipeline
   static const bool occ3_on = [] { const char* e = getenv("VBT_MB_OCC3"); return !(e && e[0] == '0'); }();
   const bool occ3 = occ3_on && cols <= 128 && smem <= 72 * 1024;
+  // one CTA per SM (512 TMEM columns or > 113 KB of shared memory): sixteen warps instead of eight hide the
+  // latency chains of the epilogues and the depthwise that a second resident CTA would otherwise cover
+  static const bool wide_on = [] { const char* e = getenv("VBT_MB_WIDE"); return e && e[0] == '1'; }();   // measured neutral: off
+  const bool wide = wide_on && !occ3 && (cols > 256 || smem > 113 * 1024);
   void (*kern)(MbArgs, CUtensorMap);
-  if (occ3) kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 3> : mbconv_umma_kernel<3, 2, 3>)
-                          : (S == 1 ? mbconv_umma_kernel<5, 1, 3> : mbconv_umma_kernel<5, 2, 3>);
-  else kern = K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, 2> : mbconv_umma_kernel<3, 2, 2>)
-                     : (S == 1 ? mbconv_umma_kernel<5, 1, 2> : mbconv_umma_kernel<5, 2, 2>);
+#define MB_PICK(M) (K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, M> : mbconv_umma_kernel<3, 2, M>) \
+                           : (S == 1 ? mbconv_umma_kernel<5, 1, M> : mbconv_umma_kernel<5, 2, M>))
+  kern = occ3 ? MB_PICK(3) : (wide ? MB_PICK(1) : MB_PICK(2));
+  const int n_threads = wide ? 512 : 256;
   static bool attr_set = false;
   if (!attr_set) {
-    void (*all[8])(MbArgs, CUtensorMap) = {mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
-                              mbconv_umma_kernel<3, 1, 3>, mbconv_umma_kernel<3, 2, 3>, mbconv_umma_kernel<5, 1, 3>, mbconv_umma_kernel<5, 2, 3>};
+    void (*all[12])(MbArgs, CUtensorMap) = {
+        mbconv_umma_kernel<3, 1, 1>, mbconv_umma_kernel<3, 2, 1>, mbconv_umma_kernel<5, 1, 1>, mbconv_umma_kernel<5, 2, 1>,
+        mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
+        mbconv_umma_kernel<3, 1, 3>, mbconv_umma_kernel<3, 2, 3>, mbconv_umma_kernel<5, 1, 3>, mbconv_umma_kernel<5, 2, 3>};
     for (auto k : all) VBT_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
@@ -826,7 +973,7 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(a.tiles_x * tiles_y * a.split), (unsigned)B);
-    cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cfg.blockDim = dim3(n_threads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     static const bool pdl = [] { const char* e = getenv("VBT_MB_PDL"); return !(e && e[0] == '0'); }();

@@ -579,7 +579,9 @@ def mbconv_images(cin_p, k, cout_p, e, d, p):
         if e is not None:
             consts[:m] = e['bias'][lo:hi]
             consts[32:32 + m] = e['mult'][lo:hi].view(np.int32)
-        consts[64:64 + m] = d['bias'][lo:hi]
+        # the expanded tensor is held in shared memory as UNSIGNED bytes (value + 128, dp4a.u32.s32): the
+        # depthwise bias carries the - 128 * sum(w) that undoes it
+        consts[64:64 + m] = d['bias'][lo:hi].astype(np.int64) - 128 * d['w'][lo:hi].astype(np.int64).reshape(m, -1).sum(axis=1)
         consts[96:96 + m] = d['mult'][lo:hi].view(np.int32)
         out[c, off_consts:off_consts + 512] = consts.view(np.uint8)
     return out, stride, n_chunks
