@@ -157,9 +157,11 @@ __device__ __forceinline__ void st_cluster16(uint32_t addr, uint32_t x, uint32_t
   asm volatile("st.shared::cluster.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
 }
 
+// (compiled in only for the DBG instantiations: even switched off at run time, two extra tick sites cost 5 % --
+// registers and code layout -- measured on B200)
 #define MB_TICK(i)                                                        \
   do {                                                                   \
-    if (dbg_on) { const long long now__ = clock64(); dbg_acc[i] += now__ - dbg_t; dbg_t = now__; } \
+    if (DBG && dbg_on) { const long long now__ = clock64(); dbg_acc[i] += now__ - dbg_t; dbg_t = now__; } \
   } while (0)
 
 // 16 accumulators (bias included) -> 16 int8; the packed / plain requantisation chosen once per call
@@ -311,7 +313,7 @@ __device__ __forceinline__ uint32_t byte_at(uint32_t w0, uint32_t w1, uint32_t w
   return (IDX & 3) ? (w >> (8 * (IDX & 3))) : w;
 }
 
-template <int K, int S, int MINB>
+template <int K, int S, int MINB, bool DBG>
 __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kernel(MbArgs a, const __grid_constant__ CUtensorMap tmap) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) unsigned long long bar_w[kWBuf], bar_e, bar_p[2], bar_in;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
   const uint32_t s_wbuf = s_in + a.sm_wbuf;
   const int n_chunks = (a.n_chunks - rank + split - 1) / split;     // this CTA's chunks (local index c)
   const uint32_t cs = (uint32_t)a.chan_stride;
-  const bool dbg_on = a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 64);
+  const bool dbg_on = DBG && a.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (tid == 0 || tid == 64);
   long long dbg_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long dbg_t = dbg_on ? clock64() : 0;
 
@@ -346,20 +348,6 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
                      smem_u32(&tmem_base_s)), "r"((uint32_t)a.tmem_cols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
-  if (tid == 0) {
-    for (int i = 0; i < kWBuf; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_w[i])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_e)));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[0])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[1])));
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_in)));
-    asm volatile("fence.mbarrier_init.release.cluster;\n");
-  }
-  for (int i = tid; i < a.cout_p; i += NT) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
-  asm volatile("tcgen05.fence::before_thread_sync;\n");
-  __syncthreads();                 // barriers initialised before anyone arms or polls them; TMEM base published
-  asm volatile("tcgen05.fence::after_thread_sync;\n");
-  const uint32_t tmem = tmem_base_s;
-  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   auto load_image = [&](int c) {   // one thread: one bulk copy (TMA engine) of chunk c's weight image
     const uint32_t bar = smem_u32(&bar_w[c % kWBuf]);
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)a.img_bytes) : "memory");
@@ -368,7 +356,47 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
                  "l"(a.img + (size_t)(rank + c * split) * a.img_stride), "r"((uint32_t)a.img_bytes), "r"(bar)
                  : "memory");
   };
-  if (tid == 64) { load_image(0); if (n_chunks > 1) load_image(1); }
+  // The threads that issue the first bulk copies initialise the barriers those copies signal themselves and issue
+  // at once: the copies' round trips (weights: model constants; input window: after the PDL wait) run under the
+  // TMEM allocation and the block barrier instead of behind them.
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_e)));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_p[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+  }
+  if (tid == 64) {
+    for (int i = 0; i < kWBuf; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_w[i])));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    load_image(0);
+    if (n_chunks > 1) load_image(1);
+  }
+  if (tid == 96) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_in)));
+    asm volatile("fence.mbarrier_init.release.cluster;\n");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    if (a.has_expand && a.use_tma && !a.stem) {
+      // -> position-major planes, the expand GEMM's A operand, by TMA: the activation tensor is described to
+      // the copy engine as [B][H][W][cin_p] bytes; one tiled load per 16-channel group drops the group's
+      // WH x WW window (16-byte rows) exactly where the plane layout wants it -- [m = wy * WW + wx][16 B] --
+      // and fills what lies outside the image with zeros (never used: the epilogue overrides those positions).
+      vbt::pdl_wait();
+      const uint32_t bar = smem_u32(&bar_in);
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(a.g_in * a.m_total * 16)) : "memory");
+      for (int g = 0; g < a.g_in; ++g)
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+            ::"r"(s_in + (uint32_t)g * a.in_gstride), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(g * 16), "r"(ex0), "r"(ey0), "r"(b), "r"(bar)
+            : "memory");
+    }
+  }
+  for (int i = tid; i < a.cout_p; i += NT) { sPjBias[i] = a.pj_bias[i]; sPjMult[i] = a.pj_mult[i]; }
+  asm volatile("tcgen05.fence::before_thread_sync;\n");
+  __syncthreads();                 // barriers initialised before anyone arms or polls them; TMEM base published
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
   vbt::pdl_wait();
   vbt::pdl_launch_dependents();
 
@@ -433,19 +461,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
       for (int k = 27; k < 32; ++k) st_shared8(d1 + (uint32_t)(k & 15), 0u);
     }
   } else if (a.has_expand && a.use_tma) {
-    // -> position-major planes, the expand GEMM's A operand, by TMA: the activation tensor is described to
-    // the copy engine as [B][H][W][cin_p] bytes; one tiled load per 16-channel group drops the group's
-    // WH x WW window (16-byte rows) exactly where the plane layout wants it -- [m = wy * WW + wx][16 B] --
-    // and fills what lies outside the image with zeros (never used: EE overrides those positions).
-    if (tid == 96) {
-      const uint32_t bar = smem_u32(&bar_in);
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(a.g_in * a.m_total * 16)) : "memory");
-      for (int g = 0; g < a.g_in; ++g)
-        asm volatile(
-            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
-            ::"r"(s_in + (uint32_t)g * a.in_gstride), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(g * 16), "r"(ex0), "r"(ey0), "r"(b), "r"(bar)
-            : "memory");
-    }
+    // the window arrives by TMA, issued in the prologue (thread 96)
   } else if (a.has_expand) {       // the same by per-thread cp.async (VBT_MB_TMA=0, or no tensor map could be encoded)
     const int G = a.g_in;
     const int8_t* fin = a.in + (size_t)b * a.H * a.W * a.cin_p;
@@ -934,20 +950,23 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   static const bool wide_on = [] { const char* e = getenv("VBT_MB_WIDE"); return e && e[0] == '1'; }();   // measured neutral: off
   const bool wide = wide_on && !occ3 && (cols > 256 || smem > 113 * 1024);
   void (*kern)(MbArgs, CUtensorMap);
-#define MB_PICK(M) (K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, M> : mbconv_umma_kernel<3, 2, M>) \
-                           : (S == 1 ? mbconv_umma_kernel<5, 1, M> : mbconv_umma_kernel<5, 2, M>))
-  kern = occ3 ? MB_PICK(3) : (wide ? MB_PICK(1) : MB_PICK(2));
-  const int n_threads = wide ? 512 : 256;
+  static const bool dbg = [] { const char* e = getenv("VBT_MB_DBG"); return e && e[0] == '1'; }();
+#define MB_PICK(M, D) (K == 3 ? (S == 1 ? mbconv_umma_kernel<3, 1, M, D> : mbconv_umma_kernel<3, 2, M, D>) \
+                              : (S == 1 ? mbconv_umma_kernel<5, 1, M, D> : mbconv_umma_kernel<5, 2, M, D>))
+  if (dbg) kern = occ3 ? MB_PICK(3, true) : MB_PICK(2, true);          // the counters exist for the 256-thread builds only
+  else kern = occ3 ? MB_PICK(3, false) : (wide ? MB_PICK(1, false) : MB_PICK(2, false));
+  const int n_threads = (wide && !dbg) ? 512 : 256;
   static bool attr_set = false;
   if (!attr_set) {
-    void (*all[12])(MbArgs, CUtensorMap) = {
-        mbconv_umma_kernel<3, 1, 1>, mbconv_umma_kernel<3, 2, 1>, mbconv_umma_kernel<5, 1, 1>, mbconv_umma_kernel<5, 2, 1>,
-        mbconv_umma_kernel<3, 1, 2>, mbconv_umma_kernel<3, 2, 2>, mbconv_umma_kernel<5, 1, 2>, mbconv_umma_kernel<5, 2, 2>,
-        mbconv_umma_kernel<3, 1, 3>, mbconv_umma_kernel<3, 2, 3>, mbconv_umma_kernel<5, 1, 3>, mbconv_umma_kernel<5, 2, 3>};
+    void (*all[20])(MbArgs, CUtensorMap) = {
+        mbconv_umma_kernel<3, 1, 1, false>, mbconv_umma_kernel<3, 2, 1, false>, mbconv_umma_kernel<5, 1, 1, false>, mbconv_umma_kernel<5, 2, 1, false>,
+        mbconv_umma_kernel<3, 1, 2, false>, mbconv_umma_kernel<3, 2, 2, false>, mbconv_umma_kernel<5, 1, 2, false>, mbconv_umma_kernel<5, 2, 2, false>,
+        mbconv_umma_kernel<3, 1, 3, false>, mbconv_umma_kernel<3, 2, 3, false>, mbconv_umma_kernel<5, 1, 3, false>, mbconv_umma_kernel<5, 2, 3, false>,
+        mbconv_umma_kernel<3, 1, 2, true>, mbconv_umma_kernel<3, 2, 2, true>, mbconv_umma_kernel<5, 1, 2, true>, mbconv_umma_kernel<5, 2, 2, true>,
+        mbconv_umma_kernel<3, 1, 3, true>, mbconv_umma_kernel<3, 2, 3, true>, mbconv_umma_kernel<5, 1, 3, true>, mbconv_umma_kernel<5, 2, 3, true>};
     for (auto k : all) VBT_CHECK_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  static const bool dbg = [] { const char* e = getenv("VBT_MB_DBG"); return e && e[0] == '1'; }();
   static long long* dbg_buf = nullptr;
   a.dbg = nullptr;
   if (dbg) {

@@ -21,6 +21,7 @@ namespace {
 constexpr int kMaxT = 256;  // live tracks per video (compile-time ceiling)
 constexpr int kMaxD = 32;   // detections per frame
 constexpr int NX = 7, NZ = 4;
+constexpr int kMaxF = 512;  // frames per launch whose counts / numbers are staged in shared memory
 constexpr int NP = 13;      // stored covariance entries, see below
 
 // The covariance of this filter never leaves a block structure: P0, Q and R are diagonal,
@@ -340,6 +341,10 @@ __device__ int assign_min_cost_warp(const double* cost, int ld, int n, int m, in
   u_s[lane] = 0.0;
   __syncwarp();
   const bool col = lane >= 1 && lane <= M;
+  // lanes 0 .. M hold everything: the arg-min runs over the smallest power of two P > M lanes, lane 0 hands the
+  // result to the lanes above P
+  int P = 2;
+  while (P <= M) P <<= 1;
   for (int i = 1; i <= N; ++i) {
     if (lane == 0) p = i;
     int j0 = 0;
@@ -356,14 +361,14 @@ __device__ int assign_min_cost_warp(const double* cost, int ld, int n, int m, in
         key = minv;
       }
       int j1 = (key < INFINITY) ? lane : 0;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
+      for (int o = P >> 1; o > 0; o >>= 1) {
         const double k2 = __shfl_xor_sync(full, key, o);
         const int jj = __shfl_xor_sync(full, j1, o);
         // candidates carry j1 == 0 when their key is not finite-below-inf
         const bool take = (jj != 0) && (j1 == 0 || k2 < key || (k2 == key && jj < j1));
         if (take) { key = k2; j1 = jj; }
       }
+      if (P < 32) { key = __shfl_sync(full, key, 0); j1 = __shfl_sync(full, j1, 0); }
       if (j1 == 0) return -1;
       const double delta = key;
       __syncwarp();
@@ -424,6 +429,7 @@ struct Shared {                 // carved from dynamic shared memory, ld = max_t
   Trk* cache;                   // [kCache] low slots of this video's track table
   Video* vid;                   // this video's list state
   double u[32];                 // row potentials of the warp-parallel assignment
+  int cnt[kMaxF], fno[kMaxF];   // detection count / frame number of every frame of this launch
   int n_pairs, n_un_d, n_un_t;
 };
 
@@ -446,10 +452,11 @@ __device__ long long g_trk_dbg[12];
 __device__ int g_trk_dbg_on;
 #define TRK_TICK(i)                                                                          \
   do {                                                                                       \
-    if (dbg) { const long long n__ = clock64(); g_trk_dbg[i] += n__ - dbg_t; dbg_t = n__; }   \
+    if (DBG && dbg) { const long long n__ = clock64(); g_trk_dbg[i] += n__ - dbg_t; dbg_t = n__; }   \
   } while (0)
 
-__global__ void __launch_bounds__(32) tracker_update_kernel(
+template <bool DBG>
+__global__ void __maxnreg__(255) tracker_update_kernel(
     Video* videos, Trk* tracks, Params prm, const double* dets, const int32_t* det_count,
     const int32_t* frame_no, const double* fps, const int32_t* n_frames, int F, int max_det, int max_tracks,
     double* rows, int32_t* row_count, int row_cap, double* last_out, int32_t* last_out_count,
@@ -458,7 +465,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
   __shared__ Shared sh;
   const unsigned full = 0xffffffffu;
   const int v = blockIdx.x, lane = threadIdx.x;
-  const bool dbg = g_trk_dbg_on && v == 0 && lane == 0;
+  const bool dbg = DBG && g_trk_dbg_on && v == 0 && lane == 0;
   long long dbg_t = dbg ? clock64() : 0;
   if (lane == 0) {
     unsigned char* p = dyn_smem;
@@ -512,10 +519,17 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
   // detections of the next frame are fetched while the current one is processed
   int nxt_n = 0;
   double nxt_d[6] = {0, 0, 0, 0, 0, 0};
+  // a dependent global load per frame (count -> which lanes load a detection; frame number -> time stamp) would
+  // sit on the recurrence's critical path: both tables are staged once per launch
+  const bool staged = nf <= kMaxF;
+  if (staged) {
+    for (int i = lane; i < nf; i += 32) { sh.cnt[i] = det_count[(size_t)v * F + i]; sh.fno[i] = frame_no[(size_t)v * F + i]; }
+    __syncwarp();
+  }
   auto fetch = [&](int f) {
     nxt_n = 0;
     if (f < nf) {
-      nxt_n = min(det_count[(size_t)v * F + f], max_det);
+      nxt_n = min(staged ? sh.cnt[f] : det_count[(size_t)v * F + f], max_det);
       if (lane < nxt_n) {
         const double* fd = dets + (((size_t)v * F + f) * max_det + lane) * 6;
 #pragma unroll
@@ -577,7 +591,8 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     __syncwarp();
     TRK_TICK(2);
     // ---- first association round ----------------------------------------------------
-    for (int i = lane; i < nd * nt; i += 32) {
+    const int n_pairs_all = nd * nt;
+    for (int i = lane; i < n_pairs_all; i += 32) {
       const int d = i / nt, t = i - d * nt;
       sh.iou[d * ld + t] = iou_of(sh.dets[d], sh.tbox[t]);
     }
@@ -607,8 +622,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
         }
       } else {
         const double kPi = 3.141592653589793;
-        for (int i = lane; i < nd * nt; i += 32) {
-          const int d = i / nt, t = i - d * nt;
+        auto pair_cost = [&](int d, int t) -> double {
           const Trk& tk = T(vid.order[t]);
           const double* prev = k_previous(tk, prm.delta_t);
           double pb[5] = {-1.0, -1.0, -1.0, -1.0, -1.0};
@@ -625,7 +639,11 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
           double valid = (pb[4] >= 0) ? 1.0 : 0.0;
           double mult = prm.vdc_cls ? sh.dets[d][5] : sh.dets[d][4];
           double angle_cost = ((valid * ang) * prm.inertia) * mult;
-          sh.cost[d * ld + t] = -(sh.iou[d * ld + t] + angle_cost);
+          return -(sh.iou[d * ld + t] + angle_cost);
+        };
+        for (int i = lane; i < n_pairs_all; i += 32) {
+          const int d = i / nt, t = i - d * nt;
+          sh.cost[d * ld + t] = pair_cost(d, t);
         }
         __syncwarp();
         int np = 0;
@@ -781,7 +799,7 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     TRK_TICK(8);
     // ---- output rows in reverse list order, then deaths -------------------------------------
     {
-      const double time = (double)frame_no[(size_t)v * F + f] / vfps;     // track.py:169
+      const double time = (double)(staged ? sh.fno[f] : frame_no[(size_t)v * F + f]) / vfps;     // track.py:169
       const bool last_frame = (f == nf - 1);
       int n_out = 0;
       for (int top = nt - 1; top >= 0; top -= 32) {
@@ -846,8 +864,9 @@ __global__ void __launch_bounds__(32) tracker_update_kernel(
     }
     __syncwarp();
     TRK_TICK(9);
-    if (dbg) g_trk_dbg[11] += 1;
+    if (DBG && dbg) g_trk_dbg[11] += 1;
   }
+  __threadfence();                                  // rows before their count: the velocity kernel may run beside the next launch
   if (lane == 0) { vid.frame_count = frame_count; row_count[v] = rc; }
   {                                                 // write the staged state back
     __syncwarp();
@@ -920,8 +939,9 @@ int vbt_tracker_create(int V, int max_tracks, const vbt_tracker_params* p, vbt_t
   t->prm.delta_t = p->delta_t; t->prm.vdc_cls = p->vdc_uses_class_column;
   VBT_CHECK_CUDA(cudaMalloc(&t->videos, sizeof(Video) * (size_t)V));
   VBT_CHECK_CUDA(cudaMalloc(&t->tracks, sizeof(Trk) * (size_t)V * max_tracks));
-  VBT_CHECK_CUDA(cudaFuncSetAttribute(tracker_update_kernel,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VBT_CHECK_CUDA(cudaFuncSetAttribute(tracker_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)shared_bytes(kMaxT)));
+  VBT_CHECK_CUDA(cudaFuncSetAttribute(tracker_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)shared_bytes(kMaxT)));
   VBT_CHECK_CUDA(cudaMalloc(&t->peek, sizeof(double) * (kMaxT * 9)));
   VBT_CHECK_CUDA(cudaMalloc(&t->scratch, sizeof(int32_t) * (size_t)(V + 1)));
@@ -957,8 +977,8 @@ int vbt_tracker_update(vbt_tracker* t, const double* dev_dets, const int32_t* de
     if (on) cudaMemcpyToSymbol(g_trk_dbg_on, &on, sizeof(int));
     return on != 0;
   }();
-  (void)dbg;
-  tracker_update_kernel<<<t->V, 32, shared_bytes(t->max_tracks), (cudaStream_t)stream>>>(
+  auto kern = dbg ? tracker_update_kernel<true> : tracker_update_kernel<false>;   // phase counters: their own build
+  kern<<<t->V, 32, shared_bytes(t->max_tracks), (cudaStream_t)stream>>>(
       t->videos, t->tracks, t->prm, dev_dets, dev_det_count, dev_frame_no, dev_fps, dev_n_frames,
       F, max_det, t->max_tracks, dev_rows, dev_row_count, row_cap, dev_last_out, dev_last_out_count,
       t->row_details);

@@ -33,6 +33,10 @@ class _VideoState:
         # video gets its own (high-priority) stream, so the tail of one video's recurrence runs
         # beside the head of the next one's instead of in front of it
         self.side = t.cuda.Stream(priority=-1)
+        # K8 (velocity lanes) of batch i only needs K7's rows of batch i: on its own stream it runs beside K7 of
+        # batch i + 1 instead of in front of it (the tracker writes rows before their count, velocity.cu reads
+        # [lane_begin, row_count) -- whichever count it sees, the rows below it are complete)
+        self.side2 = t.cuda.Stream(priority=-1)
         self.d_fps = t.full((n_videos,), float(fps), dtype=t.float64, device='cuda')
         self.tracker = BatchedTracker(n_videos, row_cap=row_cap, keep_details=keep_details, **(tracker_kw or {}))
         self.lanes = _Lanes(n_videos * id_lanes, path_cap=min(row_cap, 1 << 15))
@@ -149,6 +153,7 @@ class VideoPipeline:
             cur.wait_stream(s)
         for st in self.states:
             cur.wait_stream(st.side)
+            cur.wait_stream(st.side2)
 
     def reset(self, fps=None):
         t = self.torch
@@ -166,6 +171,7 @@ class VideoPipeline:
             s.wait_stream(cur)
         for st in self.states:
             st.side.wait_stream(cur)
+            st.side2.wait_stream(cur)
 
     def process(self, frames, frame_numbers, swap_rb=True, track=True):
         """frames: uint8 CUDA [n,H,W,3] (n <= detector.max_batch); frame_numbers: int32 CUDA
@@ -240,12 +246,17 @@ class VideoPipeline:
             self.tracker.update(self.dets[k, 0, :n].view(self.V, f, -1, 6), self.det_count[k, 0, :n].view(self.V, f),
                                 self.frame_no[k, 0, :n].view(self.V, f), self.d_fps, self.n_frames[k], stream=side)
             self._mark(marks, side)
+            self.slot_free[k].record(side)
+            tracked = t.cuda.Event()
+            tracked.record(side)
+        side2 = self.states[self.cur].side2
+        side2.wait_event(tracked)
+        with t.cuda.stream(side2):
             self.lanes.update(self.tracker.rows, self.tracker.row_count, self.tracker.row_cap,
                               self.lane_table, self.lane_id, self.lane_begin, self.n_velocity_lanes,
                               self.plate_diameter, self.diff_threshold, self.min_distance,
                               smooth=True, finish=False)
-            self._mark(marks, side)
-            self.slot_free[k].record(side)
+            self._mark(marks, side2)
         if marks is not None:
             self.stage_events.append(marks)
         self.frames_done += n
@@ -309,13 +320,14 @@ class VideoPipeline:
         what `finish()` would have returned; a set's previous handle is collected before reuse."""
         t = self.torch
         st = self.states[self.cur]
-        with t.cuda.stream(st.side):
+        st.side2.wait_stream(st.side)
+        with t.cuda.stream(st.side2):
             st.lanes.update(st.tracker.rows, st.tracker.row_count, st.tracker.row_cap,
                             st.lane_table, self.lane_id, st.lane_begin, self.n_velocity_lanes,
                             self.plate_diameter, self.diff_threshold, self.min_distance,
                             smooth=True, finish=True)
             done = t.cuda.Event()
-            done.record(st.side)
+            done.record(st.side2)
         st.pending = pending = _PendingVideo(self, st, done)
         self.cur ^= 1
         nxt = self.states[self.cur]
