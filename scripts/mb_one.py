@@ -31,4 +31,4 @@ for i in idx:
         b.record()
         st.synchronize()
     out.append(a.elapsed_time(b) * 50.0)
-print(os.environ.get('VBT_MB_EE', '-'), ' '.join(f'{v:7.1f}' for v in out), f'sum {sum(out):.1f}')
+print(' '.join(f'{v:7.1f}' for v in out), f'sum {sum(out):.1f}')

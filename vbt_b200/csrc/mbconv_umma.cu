@@ -65,7 +65,6 @@ struct MbArgs {
   int row_stride, chan_stride;               // planar expanded planes: bytes per window row / per channel
   uint32_t inv_ww, inv_twp, inv_gin, inv_sx; // ceil(2^32 / d)
   int zp_fill;                               // zero point of the depthwise input (padding value)
-  int ee_mode;                               // experiment switches (VBT_MB_EE)
   int ex_off, ex_span, ex_ulo;               // expand epilogue, packed clamp: relu(min(bits + ex_off, ex_span)) + ex_ulo = value + 128
   vbt::Requant ex_rq, dw_rq, pj_rq;
   int pj_zp, res_zp, add_mult0, add_mult1, add_shift, zp_final, lo, hi;
@@ -164,20 +163,6 @@ __device__ __forceinline__ void st_cluster16(uint32_t addr, uint32_t x, uint32_t
     if (DBG && dbg_on) { const long long now__ = clock64(); dbg_acc[i] += now__ - dbg_t; dbg_t = now__; } \
   } while (0)
 
-// 16 accumulators (bias included) -> 16 int8; the packed / plain requantisation chosen once per call
-__device__ __forceinline__ uint4 requant16r(const int (&v)[16], const vbt::Requant& rq, const float (&m)[16]) {
-  uint32_t p[4];
-  if (rq.fast) {
-#pragma unroll
-    for (int w4 = 0; w4 < 4; ++w4)
-      p[w4] = rq.pack4t<true>(v[w4 * 4], v[w4 * 4 + 1], v[w4 * 4 + 2], v[w4 * 4 + 3], m[w4 * 4], m[w4 * 4 + 1], m[w4 * 4 + 2], m[w4 * 4 + 3]);
-  } else {
-#pragma unroll
-    for (int w4 = 0; w4 < 4; ++w4)
-      p[w4] = rq.pack4t<false>(v[w4 * 4], v[w4 * 4 + 1], v[w4 * 4 + 2], v[w4 * 4 + 3], m[w4 * 4], m[w4 * 4 + 1], m[w4 * 4 + 2], m[w4 * 4 + 3]);
-  }
-  return make_uint4(p[0], p[1], p[2], p[3]);
-}
 // 16 int32 / float constants of this thread's channel half from the chunk image
 __device__ __forceinline__ void load16(uint32_t addr, int (&o)[16]) {
 #pragma unroll
@@ -576,11 +561,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     MB_TICK(1);
     // ---- EE: expand epilogue -> the chunk's expanded tensor, channel-planar ----------------------------
     if (a.has_expand) {
-      if (a.ee_mode & 2) {
-        mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));
-        if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
-        if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
-      } else if (warp == 0) {
+      if (warp == 0) {
         if (c == 0) mbar_wait(smem_u32(&bar_w[0]), 0);
         if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
         mbar_wait(smem_u32(&bar_e), par_e);
@@ -599,7 +580,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
         e.pos = &sPos[0][row]; e.n_win = a.n_win_tiles; e.wt0 = tgrp; e.wt_step = NT / 256;
         e.window_mask = window_mask; e.inside_mask = inside_mask; e.zpu = zpu;
         e.off = a.ex_off; e.span = a.ex_span; e.ulo = a.ex_ulo; e.fast = a.ex_rq.fast; e.store_next = c + 1 < n_chunks;
-        switch ((a.ee_mode & 1) ? 0u : cs) {
+        switch (cs) {
           case 12: ee_tiles<12>(e, a.ex_rq, em, eb); break;
           case 20: ee_tiles<20>(e, a.ex_rq, em, eb); break;
           case 28: ee_tiles<28>(e, a.ex_rq, em, eb); break;
@@ -832,8 +813,6 @@ int launch_mbconv_umma(const vbt_model* m, const OpRecord* ex, const OpRecord& d
   if (!ex && (a.n_chunks != 1 || a.has_res)) return VBT_OK;
   if (a.has_res && (S != 1 || !ex || a.stem || pj.cout_p != ex->cin_p)) return VBT_OK;
   a.zp_fill = dw.zp_in[0];
-  static const int ee_mode = [] { const char* e = getenv("VBT_MB_EE"); return e ? atoi(e) : 0; }();
-  a.ee_mode = ee_mode;
   a.ex_off = a.ex_span = a.ex_ulo = 0;
   if (ex) {
     a.ex_rq = Requant(ex->zp_out, ex->act_lo, ex->act_hi, ex->requant_fast);
