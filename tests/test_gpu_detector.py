@@ -285,3 +285,40 @@ def test_interpreter_loads_a_tflite_file(tmp_path):
             assert np.array_equal(p['bounding_box'], q['bounding_box']) and p['score'] == q['score']
     with pytest.raises(ValueError):
         Interpreter(model_path=str(tmp_path / 'missing.tflite'))
+
+
+@pytest.mark.gpu
+def test_model_blob_with_out_of_range_offsets_is_refused():
+    """vbt_model_create checks every weight / bias / multiplier region and every tensor extent of the blob
+    (a truncated .vbtm or a bad conversion must fail at load time, not inside a kernel)."""
+    import struct
+    import ctypes
+    from vbt_b200 import _lib, effdet
+    g = effdet.build_synthetic('lite0')
+    blob = bytearray(effdet.pack_blob(g))
+    L = _lib.lib()
+
+    def create(b):
+        h = ctypes.c_void_p()
+        rc = L.vbt_model_create(bytes(b), len(b), ctypes.byref(h))
+        if rc == 0:
+            L.vbt_model_destroy(h)
+        return rc
+
+    assert create(blob) == 0
+    # first op record starts right after the 128-byte header; its w_off is the first int64 after 30 int32
+    hdr = 128
+    rec0 = bytes(blob[hdr:hdr + 224])
+    w_off_pos = hdr + struct.calcsize('<i3ii i ii ii ii iiii 3i i ii ii')
+    bad = bytearray(blob)
+    struct.pack_into('<q', bad, w_off_pos, 1 << 40)
+    assert create(bad) == _lib.EFORMAT
+    # a tensor pushed past the per-frame workspace
+    n_ops = struct.unpack_from('<i', blob, 24)[0]
+    t0 = hdr + 224 * n_ops
+    bad = bytearray(blob)
+    struct.pack_into('<q', bad, t0, 1 << 40)
+    assert create(bad) == _lib.EFORMAT
+    # a truncated file
+    assert create(blob[:len(blob) // 2]) == _lib.EFORMAT
+    assert rec0 == bytes(blob[hdr:hdr + 224])

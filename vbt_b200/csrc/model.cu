@@ -52,7 +52,7 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
   }
   const size_t table = sizeof(BlobHeader) + sizeof(OpRecord) * (size_t)hdr.n_ops +
                        sizeof(TensorRecord) * (size_t)hdr.n_tensors;
-  if (hdr.n_ops < 0 || hdr.n_tensors < 0 || hdr.data_offset < (int64_t)table ||
+  if (hdr.n_ops < 0 || hdr.n_tensors < 0 || hdr.data_bytes < 0 || hdr.ws_bytes_per_frame < 0 || hdr.data_offset < (int64_t)table ||
       (size_t)(hdr.data_offset + hdr.data_bytes) > blob_bytes || hdr.n_anchors <= 0 ||
       hdr.n_anchors_pad < hdr.n_anchors || hdr.n_anchors_pad % 16 != 0) {
     set_error("vbt_model_create: inconsistent blob header");
@@ -82,6 +82,39 @@ int vbt_model_create(const void* blob, size_t blob_bytes, vbt_model** out) {
     if (!ok) {
       delete m;
       set_error("vbt_model_create: op references a tensor outside the table");
+      return VBT_EFORMAT;
+    }
+  }
+  // every data region an op names lies inside the data section, every tensor inside the per-frame workspace: a
+  // truncated or malformed .vbtm / converted .tflite is refused here instead of sending a kernel out of bounds
+  for (const OpRecord& op : m->ops) {
+    bool ok = true;
+    size_t wbytes = 0;
+    if (op.type == OP_STEM) wbytes = (size_t)9 * op.cout_p * 4;                 // [9 taps][cout_p] words
+    else if (op.type == OP_PW) wbytes = (size_t)op.cout_p * op.cin_p;
+    else if (op.type == OP_DW) wbytes = (size_t)op.k * op.k * op.cout_p * 4;    // [k * k][c_p] words
+    if (wbytes) {
+      ok = op.cout_p > 0 && op.cout_p % 16 == 0 && op.k >= 1 && op.k <= 7 && in_data(op.w_off, wbytes) && in_data(op.bias_off, sizeof(int32_t) * (size_t)op.cout_p) &&
+           in_data(op.scale_off, sizeof(float) * (size_t)op.cout_p);
+      if (ok && op.type == OP_PW && op.lut_off >= 0) ok = in_data(op.lut_off, 256);
+      if (ok && op.type == OP_DW && op.lut_off >= 0)
+        ok = in_data(op.lut_off, (size_t)((op.cout_p / 16 + 1) / 2) * (size_t)(op.k * op.k) * 1024);
+      if (ok && op.type == OP_DW && op.mb[0] > 0)
+        ok = op.mb[1] > 0 && op.mb[2] > 0 && in_data((int64_t)(op.mb[0] - 1) * 256, (size_t)op.mb[1] * (size_t)op.mb[2]);
+    }
+    if (!ok) {
+      delete m;
+      set_error("vbt_model_create: op '%d' names weights / bias / multipliers outside the %lld-byte data section", (int)op.type,
+                (long long)hdr.data_bytes);
+      return VBT_EFORMAT;
+    }
+  }
+  for (const TensorRecord& t : m->tensors) {
+    const long long bytes = (long long)t.h * t.w * t.c_p;
+    if (t.h < 0 || t.w < 0 || t.c_p < 0 || t.c_p % 16 != 0 || (t.ws_offset >= 0 && t.ws_offset + bytes > hdr.ws_bytes_per_frame)) {
+      delete m;
+      set_error("vbt_model_create: a %dx%dx%d tensor at workspace offset %lld does not fit the %lld bytes per frame", t.h, t.w, t.c_p,
+                (long long)t.ws_offset, (long long)hdr.ws_bytes_per_frame);
       return VBT_EFORMAT;
     }
   }
