@@ -169,10 +169,12 @@ def score_to_q(threshold):
 class Interpreter:
     """tflite_runtime.interpreter.Interpreter look-alike over `Detector` (batch 1)."""
 
-    def __init__(self, model_path=None, num_threads=None, **_ignored):
+    def __init__(self, model_path=None, num_threads=None, max_batch=1, **_ignored):
+        """max_batch (not a TFLite argument): frames per call the detector's buffers are sized for; the
+        track CLI passes its --batch here so that the model is loaded once, not once more inside track()."""
         self.model_path = model_path
         self.num_threads = num_threads           # accepted for drop-in; the GPU path ignores it
-        self._det = Detector(model_path, max_batch=1)
+        self._det = Detector(model_path, max_batch=max(1, int(max_batch)))
 
     def allocate_tensors(self):
         return None                              # buffers are allocated with the model

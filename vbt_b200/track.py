@@ -149,7 +149,7 @@ def main(src, model, detection_treshold, display_image_height, df_dir, video_dir
     for s in src:
         if not os.path.isfile(s):
             raise FileNotFoundError()
-        interpreter = Interpreter(model_path=model, num_threads=threads)
+        interpreter = Interpreter(model_path=model, num_threads=threads, max_batch=batch)   # one model load per video
         interpreter.allocate_tensors()
         video_path = None
         if video_dir is not None:
