@@ -616,7 +616,20 @@ def main():
     # Roofline of the dominant kernel CLASS that has one (HBM-bound by arithmetic intensity); K7 / K8 are
     # latency-bound recurrences (one warp per video): they enter the choice of `dominant_by_time` with
     # bound "latency" and no roofline fraction.
-    bound_of = {n: ('latency' if kern[n]['bytes_per_frame'] == 0 else 'hbm') for n in kern}
+    ridge = tf_peak * 1e12 / (hbm_peak * 1e9)
+
+    def roof_of(n):          # the roof a kernel class sits under by its ALGORITHMIC intensity
+        k = kern[n]
+        if k['bytes_per_frame'] == 0:
+            return 'latency'
+        return 'tensor' if k['flops_per_frame'] / k['bytes_per_frame'] > ridge else 'hbm'
+    bound_of = {n: roof_of(n) for n in kern}
+    # what actually limits each class as measured (ncu warp states, phase counters: DESIGN.md 4.1) -- the roofs
+    # above are where the work would be bounded if the kernels were throughput bound
+    limited_by = {'mbconv_fused': 'latency / synchronisation at 16 resident warps per SM (issue 51-60 %, tensor pipe 1-7 %, DRAM 1-2 %)',
+                  'node_fused': 'latency: ~10 us per launch on maps of <= 400 positions (prologue, fill, 18 serial tap MMAs, two epilogues)',
+                  'K7_tracker': 'latency: one warp, a chain of dependent fp64 operations per frame',
+                  'K8_velocity': 'latency: one lane per (video, id)', 'K1_preprocess': 'HBM (0.58 of the measured peak on touched rows)'}
     by_time = max(kern, key=lambda n: kern[n]['ms'])
     dom_name = max((n for n in kern if kern[n]['bytes_per_frame'] > 0), key=lambda n: kern[n]['ms'])
     dom = kern[dom_name]
@@ -636,7 +649,6 @@ def main():
     # which roof bounds the kernel by its algorithmic intensity: a fused MBConv block moves so few bytes
     # (input + output + weights; the 6x expanded tensor stays on chip) that it sits right of the ridge
     dom_tf = dom['flops_per_frame'] * frames_prof / (dom['ms'] / 1e3) / 1e12 if dom['ms'] > 0 else 0.0
-    ridge = tf_peak * 1e12 / (hbm_peak * 1e9)
     intensity = dom['flops_per_frame'] / max(dom['bytes_per_frame'], 1)
     tensor_bound = intensity > ridge
     roofline = {'kernel': dom_name, 'bound': 'tensor' if tensor_bound else 'hbm',
@@ -647,13 +659,14 @@ def main():
                 'algorithmic_intensity_flop_per_byte': intensity, 'ridge_flop_per_byte': ridge,
                 'hbm_gbs_algorithmic': dom_gbs, 'hbm_frac_algorithmic': dom_gbs / hbm_peak,
                 'share_of_step': dom['ms'] / total_kernel_ms,
+                'limited_by': limited_by.get(dom_name),
                 'algorithmic_bytes_per_frame': dom['bytes_per_frame'],
                 'avg_launch_us': 1e3 * dom['ms'] / max(dom['launches_per_step'] * max(calls, 1), 1),
                 'tensor_tflops': dom_tf,
                 'dominant_by_time': {'kernel': by_time, 'bound': bound_of[by_time], 'share_of_step': kern[by_time]['ms'] / total_kernel_ms},
                 'e2e_frac': per_gpu / min(hbm_ceiling, tensor_ceiling),
                 'e2e_ceilings_frames_per_s': {'hbm': hbm_ceiling, 'tensor_bf16_sustained': tensor_ceiling}}
-    breakdown = {n: {'share': k['ms'] / total_kernel_ms, 'bound': bound_of[n],
+    breakdown = {n: {'share': k['ms'] / total_kernel_ms, 'bound': bound_of[n], 'limited_by': limited_by.get(n),
                      'gbs': (k['bytes_per_frame'] * frames_prof / (k['ms'] / 1e3) / 1e9) if k['ms'] > 0 and k['bytes_per_frame'] else None,
                      'ms_per_step': k['ms'] / max(prof_steps, 1)}
                  for n, k in sorted(kern.items(), key=lambda kv: -kv[1]['ms'])}
