@@ -11,19 +11,20 @@
 //   fill     the tile's input window (WH x WW pixels, halo included) -> shared-memory planes, one per
 //            16-channel group: [group][m][16 B], m = wy * WW + wx: the K-major core-matrix A operand
 //            of the expand GEMM.
-//   per chunk c (weights: ONE bulk copy of a host-prepared image, three buffers deep):
-//     E   expand GEMM  D_E[window positions, 32] = in planes x Wexp_c^T      (tcgen05.mma kind::i8,
-//         accumulators in TMEM), issued one chunk ahead so that it runs under the previous chunk's
-//         depthwise
-//     EE  epilogue: requantise + ReLU6 -> the chunk's expanded tensor as CHANNEL-PLANAR bytes
-//         [channel][wy][wx]; positions outside the image get the expanded tensor's zero point (TF
-//         SAME pads the depthwise INPUT, i.e. the expanded tensor)
+//   per chunk c (weights: ONE bulk copy of a host-prepared image, four buffers deep, requested two chunks ahead):
+//     E   expand GEMM  D_E[window positions, 32] = bias + in planes x Wexp_c^T   (tcgen05.mma kind::i8,
+//         accumulators in TMEM, pre-loaded with the chunk's bias by tcgen05.st), issued one chunk ahead so
+//         that it runs under the previous chunk's depthwise
+//     EE  epilogue: requantise + ReLU6 -> the chunk's expanded tensor as CHANNEL-PLANAR UNSIGNED bytes
+//         (value + 128) [window row][channel][cs bytes]; positions outside the image get the expanded tensor's
+//         zero point (TF SAME pads the depthwise INPUT, i.e. the expanded tensor).  Per value: I2F, FMUL, half
+//         a FADD2, one VIADDMNMX.RELU, one byte store at an immediate offset (ee_tiles)
 //     DW  depthwise on the SIMT pipes: lane = channel, a warp walks strips of four output pixels of
 //         one row.  In the planar layout four horizontally adjacent taps of ONE channel are the four
-//         bytes of a word, so a 5-tap row of the window is two dp4a (3-tap: one) with all lanes
-//         useful -- no masked weights, no unpacking; windows at odd byte offsets come from PRMT.  Weights
-//         (K rows x 1 or 2 words), bias and multiplier of the lane's channel stay in registers for the
-//         chunk.  Requantise + ReLU6 -> two "middle" planes [group][q][16 B] = the K-major A operand of
+//         bytes of a word, so a 5-tap row of the window is two dp4a.u32.s32 (3-tap: one) with all lanes
+//         useful -- no masked weights, no unpacking (the bias carries - 128 * sum(w)); windows at odd byte
+//         offsets come from PRMT.  Weights (K rows x 1 or 2 words), bias and multiplier of the lane's channel
+//         stay in registers for the chunk.  Requantise + ReLU6 -> two "middle" planes [group][q][16 B] = the K-major A operand of
 //         the project GEMM.  (Two other forms were built first and measured on B200: the tensor-pipe
 //         depthwise of csrc/dw_umma.cu -- block-diagonal tap matrices -- occupies the pipe ~100
 //         cycles per M128 N32 K32 tap MMA, 2,500 cycles per chunk for 5x5, on the pipe the two GEMMs
