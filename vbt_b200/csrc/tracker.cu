@@ -330,55 +330,51 @@ __device__ int assign_min_cost(const double* cost, int ld, int n, int m, int* pa
 // what the serial strict `<` scan does.  Same floating-point expressions, same result.
 // All 32 lanes must call it; returns the pair count (-1: no augmenting column).
 __device__ int assign_min_cost_warp(const double* cost, int ld, int n, int m, int* pair_r, int* pair_c,
-                                    double* u_s /* [32] shared */, int lane) {
+                                    double* scratch /* [32] shared */, int lane) {
   if (n == 0 || m == 0) return 0;
   const bool tr = n > m;
   const int N = tr ? m : n, M = tr ? n : m;
   const unsigned full = 0xffffffffu;
-  double v = 0.0, minv = INFINITY;
+  // lane j: column j (v, minv, way, used, p); lane r: row r (its potential u, whether it is on the alternating tree)
+  double v = 0.0, minv = INFINITY, u = 0.0;
   int p = 0, way = 0;
   bool used = false;
-  u_s[lane] = 0.0;
-  __syncwarp();
   const bool col = lane >= 1 && lane <= M;
-  // lanes 0 .. M hold everything: the arg-min runs over the smallest power of two P > M lanes, lane 0 hands the
-  // result to the lanes above P
-  int P = 2;
-  while (P <= M) P <<= 1;
   for (int i = 1; i <= N; ++i) {
     if (lane == 0) p = i;
     int j0 = 0;
     minv = INFINITY;
     used = false;
+    bool in_tree = false;
     while (true) {
       if (lane == j0) used = true;
       const int i0 = __shfl_sync(full, p, j0);
+      if (lane == i0) in_tree = true;   // the rows whose potential moves: p[j] of the used columns (the serial u[p[j]] += delta)
+      const double u_i0 = __shfl_sync(full, u, i0);
       double key = INFINITY;
       if (col && !used) {
         const double cij = tr ? cost[(lane - 1) * ld + (i0 - 1)] : cost[(i0 - 1) * ld + (lane - 1)];
-        const double cur = cij - u_s[i0] - v;
+        const double cur = cij - u_i0 - v;
         if (cur < minv) { minv = cur; way = j0; }
         key = minv;
       }
-      int j1 = (key < INFINITY) ? lane : 0;
-      for (int o = P >> 1; o > 0; o >>= 1) {
-        const double k2 = __shfl_xor_sync(full, key, o);
-        const int jj = __shfl_xor_sync(full, j1, o);
-        // candidates carry j1 == 0 when their key is not finite-below-inf
-        const bool take = (jj != 0) && (j1 == 0 || k2 < key || (k2 == key && jj < j1));
-        if (take) { key = k2; j1 = jj; }
-      }
-      if (P < 32) { key = __shfl_sync(full, key, 0); j1 = __shfl_sync(full, j1, 0); }
-      if (j1 == 0) return -1;
-      const double delta = key;
-      __syncwarp();
-      if (used) {                       // lanes 0..M that are on the alternating tree
-        u_s[p] += delta;                // distinct rows: p is injective over used columns
-        v -= delta;
-      } else if (col) {
-        minv -= delta;
-      }
-      __syncwarp();
+      // arg-min over the candidate columns (key below +inf), ties to the lowest column -- the serial scan's strict
+      // `<`: the keys as order-preserving 64-bit integers (-0.0 folded onto +0.0 first: equal as doubles), high
+      // words through one warp min-reduction, low words of the survivors through a second, the lowest lane of
+      // what is left by ballot.  Five dependent warp operations instead of three shuffles per halving step.
+      const bool cand = key < INFINITY;
+      const unsigned long long kb = (unsigned long long)__double_as_longlong(key + 0.0);
+      const unsigned long long ko = !cand ? ~0ull : ((kb >> 63) ? ~kb : (kb | 0x8000000000000000ull));
+      const unsigned hi = (unsigned)(ko >> 32), lo = (unsigned)ko;
+      const unsigned min_hi = __reduce_min_sync(full, hi);
+      const unsigned min_lo = __reduce_min_sync(full, hi == min_hi ? lo : 0xffffffffu);
+      const unsigned win = __ballot_sync(full, cand && hi == min_hi && lo == min_lo);
+      if (win == 0) return -1;
+      const int j1 = __ffs(win) - 1;
+      const double delta = __shfl_sync(full, key, j1);
+      if (in_tree) u += delta;
+      if (used) v -= delta;             // lanes 0..M that are on the alternating tree
+      else if (col) minv -= delta;
       j0 = j1;
       if (__shfl_sync(full, p, j0) == 0) break;
     }
@@ -391,24 +387,23 @@ __device__ int assign_min_cost_warp(const double* cost, int ld, int n, int m, in
     }
   }
   // pairs sorted by row of the ORIGINAL orientation
-  int cnt = 0;
+  int cnt;
   if (!tr) {
-    // row i-1 (i = 1..N) is matched to the column whose p == i
-    for (int i = 1; i <= N; ++i) {
-      const unsigned mask = __ballot_sync(full, col && p == i);
-      if (mask) {
-        if (lane == 0) { pair_r[cnt] = i - 1; pair_c[cnt] = __ffs(mask) - 2; }
-        ++cnt;
-      }
-    }
+    // row r (1..N) is matched to the column whose p == r: the columns post themselves at their row's slot
+    int* col_of_row = reinterpret_cast<int*>(scratch);
+    col_of_row[lane] = -1;
+    __syncwarp();
+    if (col && p != 0) col_of_row[p] = lane;
+    __syncwarp();
+    const int c = (lane >= 1 && lane <= N) ? col_of_row[lane] : -1;
+    const unsigned mask = __ballot_sync(full, c >= 0);
+    if (c >= 0) { const int pos = __popc(mask & ((1u << lane) - 1u)); pair_r[pos] = lane - 1; pair_c[pos] = c - 1; }
+    cnt = __popc(mask);
   } else {
-    for (int j = 1; j <= M; ++j) {
-      const int pj = __shfl_sync(full, p, j);
-      if (pj != 0) {
-        if (lane == 0) { pair_r[cnt] = j - 1; pair_c[cnt] = pj - 1; }
-        ++cnt;
-      }
-    }
+    const bool has = col && p != 0;     // original row = this column
+    const unsigned mask = __ballot_sync(full, has);
+    if (has) { const int pos = __popc(mask & ((1u << lane) - 1u)); pair_r[pos] = lane - 1; pair_c[pos] = p - 1; }
+    cnt = __popc(mask);
   }
   __syncwarp();
   return cnt;
@@ -448,7 +443,7 @@ __device__ __forceinline__ unsigned lanemask_lt(int lane) { return (1u << lane) 
 // lane ever walks a list alone; only births (rare, order-dependent slot allocation) and
 // the > 31-wide assignment fallback are serial.
 // VBT_TRK_DBG=1: cycles per phase of video 0 (lane 0), summed over the frames of every launch
-__device__ long long g_trk_dbg[12];
+__device__ long long g_trk_dbg[16];
 __device__ int g_trk_dbg_on;
 #define TRK_TICK(i)                                                                          \
   do {                                                                                       \
@@ -591,25 +586,27 @@ __global__ void __maxnreg__(255) tracker_update_kernel(
     __syncwarp();
     TRK_TICK(2);
     // ---- first association round ----------------------------------------------------
+    // overlaps above the threshold are counted per detection (un_d) and per track (un_t) while the matrix is
+    // written -- the index lists these arrays hold later are not built yet; pr[d] = a track d overlaps
     const int n_pairs_all = nd * nt;
+    for (int t = lane; t < nt; t += 32) sh.un_t[t] = 0;
+    if (lane < kMaxD) { sh.un_d[lane] = 0; sh.pr[lane] = -1; }
+    __syncwarp();
     for (int i = lane; i < n_pairs_all; i += 32) {
       const int d = i / nt, t = i - d * nt;
-      sh.iou[d * ld + t] = iou_of(sh.dets[d], sh.tbox[t]);
+      const double v = iou_of(sh.dets[d], sh.tbox[t]);
+      sh.iou[d * ld + t] = v;
+      if (v > thr) { atomicAdd(&sh.un_d[d], 1); atomicAdd(&sh.un_t[t], 1); sh.pr[d] = t; }
     }
     __syncwarp();
-    int rmax = 0, cmax = 0, hit_t = -1;             // hits per detection / per track
-    if (lane < nd) {
-      for (int t = 0; t < nt; ++t)
-        if (sh.iou[lane * ld + t] > thr) { ++rmax; hit_t = t; }
-    }
-    for (int t = lane; t < nt; t += 32) {
-      int c = 0;
-      for (int d = 0; d < nd; ++d) c += sh.iou[d * ld + t] > thr;
-      cmax = max(cmax, c);
-    }
+    TRK_TICK(12);
+    int rmax = lane < nd ? sh.un_d[lane] : 0, cmax = 0;   // hits per detection / per track
+    const int hit_t = lane < nd ? sh.pr[lane] : -1;       // the track, when there is exactly one
+    for (int t = lane; t < nt; t += 32) cmax = max(cmax, sh.un_t[t]);
     const int my_hits = rmax;
     rmax = __reduce_max_sync(full, rmax);
     cmax = __reduce_max_sync(full, cmax);
+    TRK_TICK(13);
     int n_pairs = 0;
     if (nt > 0 && nd > 0) {
       if (rmax == 1 && cmax == 1) {                 // every overlap is unambiguous
@@ -646,6 +643,7 @@ __global__ void __maxnreg__(255) tracker_update_kernel(
           sh.cost[d * ld + t] = pair_cost(d, t);
         }
         __syncwarp();
+        TRK_TICK(14);
         int np = 0;
         if (max(nd, nt) <= 31) {
           np = assign_min_cost_warp(sh.cost, ld, nd, nt, sh.pair_d, sh.pair_t, sh.u, lane);
@@ -655,6 +653,7 @@ __global__ void __maxnreg__(255) tracker_update_kernel(
         }
         if (np < 0) { np = 0; if (lane == 0) vid.status = VBT_EINVAL; }
         n_pairs = np;
+        TRK_TICK(15);
       }
     }
     __syncwarp();
@@ -1001,13 +1000,15 @@ int vbt_tracker_status(vbt_tracker* t, int32_t* host_status, void* stream) {
                                  cudaMemcpyDeviceToHost, st));
   VBT_CHECK_CUDA(cudaStreamSynchronize(st));
   if (getenv("VBT_TRK_DBG")) {
-    long long h[12];
+    long long h[16];
     cudaMemcpyFromSymbol(h, g_trk_dbg, sizeof(h));
     static const char* nm[10] = {"prologue", "compact dets", "predict", "assoc 1", "unmatched lists", "update matched", "OCR round",
                                  "update unmatched", "births", "output+deaths"};
     const double fr = h[11] > 0 ? (double)h[11] : 1.0;
     fprintf(stderr, "[tracker video 0: %lld frames stepped]\n", h[11]);
     for (int i = 0; i < 10; ++i) fprintf(stderr, "   %-18s %10.0f cycles/frame\n", nm[i], (double)h[i] / fr);
+    static const char* nm2[4] = {"  assoc 1: IoU", "  assoc 1: counts", "  assoc 1: costs", "  assoc 1: solver"};
+    for (int i = 0; i < 4; ++i) fprintf(stderr, "   %-18s %10.0f cycles/frame\n", nm2[i], (double)h[12 + i] / fr);
   }
   for (int v = 0; v < t->V; ++v)
     if (host_status[v] != 0) {
