@@ -534,9 +534,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     }
     umma_commit(smem_u32(&bar_e));
   };
-  if (warp_u == 1 && a.has_expand) {
-    mbar_wait(smem_u32(&bar_w[0]), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;\n");
+  if (warp_u == 1 && a.has_expand) {       // image 0: every thread polled its barrier before storing the bias
     if (elect_one()) issue_expand(0);
   }
 
@@ -562,10 +560,11 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     MB_TICK(1);
     // ---- EE: expand epilogue -> the chunk's expanded tensor, channel-planar ----------------------------
     if (a.has_expand) {
-      if (warp == 0) {
+      // two warps poll side by side (a completed try_wait still costs ~100 cycles): warp 0 the expand MMAs, warp 3 the images
+      if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
+      if (warp == 3) {
         if (c == 0) mbar_wait(smem_u32(&bar_w[0]), 0);
         if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
-        mbar_wait(smem_u32(&bar_e), par_e);
       }
       __syncthreads();
       par_e ^= 1;
@@ -604,7 +603,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     // ---- E(c + 1): runs on the tensor pipe while the SIMT pipes do this chunk's depthwise -----------------
     if (warp_u == 1 && a.has_expand && c + 1 < n_chunks) {
       asm volatile("tcgen05.fence::after_thread_sync;\n");
-      mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
+      // image c + 1: warp 3 saw its barrier before this chunk's epilogue, two block barriers ago
       if (elect_one()) issue_expand(c + 1);
     }
     MB_TICK(5);
