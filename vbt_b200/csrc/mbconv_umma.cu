@@ -560,13 +560,16 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     MB_TICK(1);
     // ---- EE: expand epilogue -> the chunk's expanded tensor, channel-planar ----------------------------
     if (a.has_expand) {
-      // two warps poll side by side (a completed try_wait still costs ~100 cycles): warp 0 the expand MMAs, warp 3 the images
-      if (warp == 0) mbar_wait(smem_u32(&bar_e), par_e);
-      if (warp == 3) {
-        if (c == 0) mbar_wait(smem_u32(&bar_w[0]), 0);
-        if (c + 1 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 1) % kWBuf]), (uint32_t)(((c + 1) / kWBuf) & 1));
+      // E(c) complete and image c + 1 landed: for c >= 1 two warps saw those barriers at the end of the previous
+      // chunk's depthwise, in front of the block barrier that closed it -- no poll and no barrier of its own here
+      if (c == 0) {
+        if (warp == 0) mbar_wait(smem_u32(&bar_e), 0);
+        if (warp == 3) {
+          mbar_wait(smem_u32(&bar_w[0]), 0);
+          if (n_chunks > 1) mbar_wait(smem_u32(&bar_w[1 % kWBuf]), 0);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       par_e ^= 1;
       asm volatile("tcgen05.fence::after_thread_sync;\n");
       MB_TICK(2);
@@ -649,6 +652,12 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
       }
     }
     MB_TICK(8);
+    // the next chunk's barriers, polled by the two warps with the fewest strips (a completed try_wait costs ~100
+    // cycles): E(c + 1) was issued at the start of this depthwise, image c + 2 a chunk ago
+    if (a.has_expand && c + 1 < n_chunks) {
+      if (warp == NT / 32 - 1) mbar_wait(smem_u32(&bar_e), par_e);
+      if (warp == NT / 32 - 2 && c + 2 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 2) % kWBuf]), (uint32_t)(((c + 2) / kWBuf) & 1));
+    }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n");
     __syncthreads();
