@@ -621,7 +621,9 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
       const float dmult = __uint_as_float(ld_shared32(consts + 384 + lane * 4));
       const uint32_t cbase = s_exp + (uint32_t)lane * cs;
       const uint32_t mbase = s_mid + (uint32_t)(c & 1) * mid_buf + (uint32_t)(lane >> 4) * a.mid_gstride + (uint32_t)(lane & 15);
-      for (int sidx = warp; sidx < a.n_strips; sidx += NT / 32) {
+      // strips are dealt starting at warp 2: when they do not divide evenly the extra ones miss warps 0 and 1,
+      // which also issue the MMAs
+      for (int sidx = (warp + NT / 32 - 2) % (NT / 32); sidx < a.n_strips; sidx += NT / 32) {
         const int ly = a.strips_x == 1 ? sidx : (int)__umulhi((uint32_t)sidx, a.inv_sx);
         const int x0 = (sidx - ly * a.strips_x) * 4;
         int acc[4] = {dbias, dbias, dbias, dbias};
