@@ -199,11 +199,6 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar_pw[tid])));
   }
   if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;\n");
-  for (int i = tid; i < Ge * 16; i += kThreads) {
-    sDwBias[i] = i < a.c_p ? a.dw_bias[i] : 0;
-    sDwMult[i] = i < a.c_p ? a.dw_mult[i] : 0.f;
-  }
-  for (int i = tid; i < a.cout_p; i += kThreads) { sPwBias[i] = a.pw_bias[i]; sPwMult[i] = a.pw_mult[i]; }
   {
     const int4* src = reinterpret_cast<const int4*>(a.wdiag);
     for (int i = tid; i < a.pairs * 9 * 64; i += kThreads)
@@ -234,6 +229,12 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
       }
     }
   }
+  // bias / multiplier vectors: plain loads (a thread stalls on them), so they follow the asynchronous weight copies
+  for (int i = tid; i < Ge * 16; i += kThreads) {
+    sDwBias[i] = i < a.c_p ? a.dw_bias[i] : 0;
+    sDwMult[i] = i < a.c_p ? a.dw_mult[i] : 0.f;
+  }
+  for (int i = tid; i < a.cout_p; i += kThreads) { sPwBias[i] = a.pw_bias[i]; sPwMult[i] = a.pw_mult[i]; }
   if (Ge > G && !a.pw_bf16)                            // pad group of the depthwise output: zeros
     for (int i = tid; i < a.n_mt * 128; i += kThreads)
       st_shared16(smem_u32(pmid) + (uint32_t)(Ge - 1) * mid_plane + (uint32_t)i * 16, make_uint4(0, 0, 0, 0));
@@ -320,17 +321,21 @@ __global__ void __launch_bounds__(kThreads) node_umma_kernel(NodeArgs a) {
   // ---- depthwise: nine shifted views per tile and group pair ----------------------------------
   if (warp_u == 0 && elect_one()) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t pbase = smem_u32(pin), wbase = smem_u32(wdw);
+    // descriptors are built once; a start address moves by adding (bytes >> 4) to the low word (everything lies
+    // below 256 KB, the 14-bit field never overflows) -- the issuing thread's arithmetic runs on the slow uniform path
+    const uint64_t adesc0 = umma_desc(smem_u32(pin), in_plane, 128);
+    const uint64_t bdesc0 = umma_desc(smem_u32(wdw), 512, 128);
     for (int mt = 0; mt < a.n_mt; ++mt) {
       for (int p = 0; p < a.pairs; ++p) {
-        int t = 0;
+        const uint64_t ad_p = adesc0 + (uint64_t)((((uint32_t)(2 * p) * in_plane) >> 4) + (uint32_t)mt * 128);
+        const uint64_t bd_p = bdesc0 + (uint64_t)((uint32_t)(p * 9) * 64);
+        const uint32_t d = tmem_u + (uint32_t)(mt * a.pairs + p) * 32;
+#pragma unroll
         for (int ky = 0; ky < 3; ++ky)
-          for (int kx = 0; kx < 3; ++kx, ++t) {
-            const uint32_t aaddr = pbase + (uint32_t)(2 * p) * in_plane +
-                                   ((uint32_t)mt * 128 + (uint32_t)(ky * a.PW + kx)) * 16;
-            umma_i8(tmem_u + (uint32_t)(mt * a.pairs + p) * 32, umma_desc(aaddr, in_plane, 128),
-                    umma_desc(wbase + (uint32_t)(p * 9 + t) * 1024, 512, 128), idesc, t > 0 ? 1u : 0u);
-          }
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx)
+            umma_i8(d, ad_p + (uint64_t)(uint32_t)(ky * a.PW + kx), bd_p + (uint64_t)((ky * 3 + kx) * 64), idesc,
+                    (ky | kx) ? 1u : 0u);
       }
       umma_commit(smem_u32(&mbar_dw[mt]));
     }
