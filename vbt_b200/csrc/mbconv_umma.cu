@@ -49,7 +49,7 @@ namespace {
 using vbt::OpRecord;
 
 constexpr int kThreads = 256;      // 8 warps: warp w owns TMEM lanes 32 * (w % 4) .., 16-channel half w / 4
-constexpr int kWBuf = 4;           // weight-image buffers: images are requested two chunks ahead
+constexpr int kWBuf = 4;           // weight-image buffers: images are requested three chunks ahead
 constexpr int kMaxCout = 352;
 
 struct MbArgs {
@@ -357,6 +357,7 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     load_image(0);
     if (n_chunks > 1) load_image(1);
+    if (n_chunks > 2) load_image(2);
   }
   if (tid == 96) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar_in)));
@@ -548,12 +549,6 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
   for (int c = 0; c < n_chunks; ++c) {
     const uint32_t wb = s_wbuf + (uint32_t)(c % kWBuf) * a.img_stride;
     const uint32_t consts = wb + a.off_consts;
-    // Buffer reuse: weight buffer (c + 2) % 4 last held chunk c - 2 and middle buffer c & 1 was last
-    // read by P(c - 2): both are free once P(c - 2) has completed (E(c - 2) did long ago).
-    if (warp_u == 2) {
-      if (c >= 2) mbar_wait(smem_u32(&bar_p[c & 1]), (uint32_t)(((c - 2) >> 1) & 1));
-      if (c + 2 < n_chunks && elect_one()) load_image(c + 2);
-    }
     // images c and c + 1 (its expand bias is stored at the end of this chunk's epilogue): ONE warp polls the
     // barriers, the block barrier below hands the visibility on (image c + 1 was requested a chunk ago)
     if (!a.has_expand) mbar_wait(smem_u32(&bar_w[c % kWBuf]), (uint32_t)((c / kWBuf) & 1));
@@ -659,6 +654,12 @@ __global__ void __launch_bounds__(MINB == 1 ? 512 : 256, MINB) mbconv_umma_kerne
     if (a.has_expand && c + 1 < n_chunks) {
       if (warp == NT / 32 - 1) mbar_wait(smem_u32(&bar_e), par_e);
       if (warp == NT / 32 - 2 && c + 2 < n_chunks) mbar_wait(smem_u32(&bar_w[(c + 2) % kWBuf]), (uint32_t)(((c + 2) / kWBuf) & 1));
+      // Buffer reuse: the middle buffer the NEXT depthwise writes and the weight buffer of image c + 3 were last read
+      // by P(c - 1), issued a whole chunk ago: one poll frees both, and the image is requested three chunks ahead
+      if (warp_u == NT / 32 - 3) {
+        if (c >= 1) mbar_wait(smem_u32(&bar_p[(c - 1) & 1]), (uint32_t)(((c - 1) >> 1) & 1));
+        if (c + 3 < n_chunks && elect_one()) load_image(c + 3);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n");
